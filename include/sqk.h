@@ -1,0 +1,165 @@
+/*
+ * sqk.h -- C ABI of libsqk.so, the B200 (sm_100a) implementation of SquiggleKit's two
+ * signal-analysis hot paths.  Plain C: pointers and sizes only, no C++/torch types, no
+ * exceptions across the boundary.  Every entry point cites the reference code it replaces
+ * (paths relative to the Psy-Fer/SquiggleKit tree).
+ *
+ * The reference has no FFI of its own: the boundary is two Python call sites,
+ *     dist, cost, path = dtw_subsequence(model[name], sig)        MotifSeq.py:437
+ *     segs = get_segs(sig, args)                                   segmenter.py:128,159,211,242,273
+ * plus the per-read preparation in front of them (outlier removal, normalisation,
+ * truncation).  libsqk batches those calls over reads.  INTEGRATION.md shows the ctypes stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - signals: all reads concatenated, int16 raw DAC samples; offsets[n_reads+1] are sample
+ *     indices into it (ragged reads, zero-length reads allowed); offsets[0] need not be 0.
+ *   - mem = SQK_MEM_HOST:   every pointer is host memory; the call is synchronous; reads are
+ *                           streamed to the GPU in chunks, copies overlapped with compute
+ *                           (pinned host memory -- sqk_host_alloc -- makes the overlap real).
+ *     mem = SQK_MEM_DEVICE: every pointer is device memory on the ctx's device; the call only
+ *                           enqueues work on the ctx stream (sqk_ctx_set_stream / sqk_ctx_sync).
+ *   - return value: 0 = ok, <0 = sqk_status; message via sqk_last_error() (thread-local).
+ *   - a ctx is bound to one device and is not thread-safe; use one ctx per host thread.
+ *   - the caller owns every buffer passed in; the library keeps no reference after return
+ *     (device mode: after the stream work has completed).
+ *   - there is NO CPU fallback: without a CUDA device sqk_ctx_create fails.
+ */
+#ifndef SQK_H
+#define SQK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQK_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define SQK_API __attribute__((visibility("default")))
+#else
+#define SQK_API
+#endif
+
+enum sqk_status {
+    SQK_OK = 0,
+    SQK_ERR_ARG = -1,         /* bad argument */
+    SQK_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    SQK_ERR_NOMEM = -3,       /* host or device allocation failed */
+    SQK_ERR_UNSUPPORTED = -4, /* valid request this build cannot serve (e.g. motif too long) */
+    SQK_ERR_OVERFLOW = -5     /* an output capacity given by the caller was exceeded */
+};
+
+enum sqk_mem { SQK_MEM_HOST = 0, SQK_MEM_DEVICE = 1 };
+
+/* MotifSeq.py:96  --scale {zscale, medmad};  "none" feeds already-centred data through */
+enum sqk_scale { SQK_SCALE_ZSCALE = 0, SQK_SCALE_MEDMAD = 1, SQK_SCALE_NONE = 2 };
+
+/* DTW arithmetic: FP64 reproduces mlpy's float64 recurrence bit for bit (indices and dist);
+ * FP32 is the fast mode (dist within 1e-4, indices may differ on near-ties: rate is reported) */
+enum sqk_precision { SQK_PREC_FP64 = 0, SQK_PREC_FP32 = 1 };
+
+typedef struct sqk_ctx sqk_ctx;
+
+SQK_API int sqk_version(void);
+SQK_API const char *sqk_last_error(void);
+
+SQK_API int sqk_ctx_create(int device, sqk_ctx **out);
+SQK_API int sqk_ctx_destroy(sqk_ctx *ctx);
+/* Run device-mode calls on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
+ * stream); NULL restores the ctx's own stream. */
+SQK_API int sqk_ctx_set_stream(sqk_ctx *ctx, void *cuda_stream);
+SQK_API int sqk_ctx_sync(sqk_ctx *ctx);
+SQK_API int sqk_device_count(int *count);
+/* multiProcessorCount etc. of the ctx device: props[0]=SMs, [1]=max smem/block (bytes),
+ * [2]=SM clock kHz, [3]=L2 bytes, [4]=compute capability major*10+minor */
+SQK_API int sqk_ctx_device_props(sqk_ctx *ctx, int64_t props[5]);
+
+/* Pinned host memory for mem=SQK_MEM_HOST callers that want copy/compute overlap. */
+SQK_API int sqk_host_alloc(uint64_t bytes, void **out);
+SQK_API int sqk_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------
+ * MotifSeq hot path.  Per read, per model -- exactly the body of the reference's main loop:
+ *     sig = scale_outliers(sig)                 MotifSeq.py:317-324  keep lo < s < hi
+ *     sig = zscale | medmad                     MotifSeq.py:186-200
+ *     dist, cost, path = dtw_subsequence(model, sig)                 MotifSeq.py:437
+ *     start = path[1][0]; end = path[1][-1]                          MotifSeq.py:438-439
+ * Indices are in the post-outlier-removal index space, as in the reference.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t scale_mode; /* enum sqk_scale */
+    int32_t lo, hi;     /* --scale_low / --scale_hi, MotifSeq.py:118-121 (defaults 0, 1200) */
+    int32_t precision;  /* enum sqk_precision */
+} sqk_motif_params;
+
+typedef struct {
+    int32_t start; /* path[1][0];  -1: read empty after outlier removal; -2: scale undefined (MAD == 0) */
+    int32_t end;   /* path[1][-1] == np.argmin(cost[-1, :]) */
+    double dist;   /* cost[-1, end]; NaN when start < 0 */
+} sqk_hit;
+
+/*
+ * models: n_models expanded motifs (float64, what read_synth_model MotifSeq.py:354-379 returns),
+ * concatenated; model_offsets[n_models+1].  models, model_offsets and params are ALWAYS host
+ * pointers (they are a few hundred bytes); `mem` describes signals, offsets, hits and n_kept.  hits is [n_reads][n_models] (read-major, the order
+ * get_region_multi MotifSeq.py:436 prints).  n_kept (optional, may be NULL): post-outlier length
+ * of each read.  max_read_len: longest read in samples if the caller knows it, 0 = let the
+ * library find out (costs one device sync in device mode).
+ */
+SQK_API int sqk_motifseq(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                 int64_t max_read_len, const double *models, const int32_t *model_offsets, int32_t n_models,
+                 const sqk_motif_params *params, int mem, sqk_hit *hits, int32_t *n_kept);
+
+/* cost[-1, :] of ONE read against ONE model (what view_region plots, MotifSeq.py:507-509) and its
+ * normalised signal (what -x prints, MotifSeq.py:447).  Host pointers.  last_row / norm_sig have
+ * capacity `cap` doubles each (either may be NULL); *n_out = post-outlier length. */
+SQK_API int sqk_motifseq_trace(sqk_ctx *ctx, const int16_t *signal, int64_t n_samples, const double *model,
+                       int32_t n_model, const sqk_motif_params *params, double *last_row, double *norm_sig,
+                       int64_t cap, int64_t *n_out, sqk_hit *hit);
+
+/* ---------------------------------------------------------------------------------------
+ * segmenter hot path.  Per read -- the body of the reference's main loop:
+ *     sig = sig[:Num]   (Num == 0 -> -1: drops the last sample)      segmenter.py:104-105,124,207
+ *     sig = scale_outliers(sig)                                      segmenter.py:311-318
+ *     segs = get_segs(sig, args)                                     segmenter.py:399-470
+ * test_segs (segmenter.py:473-494) is a two-comparison filter on the result and stays on the host.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t error;      /* -e, default 5    */
+    int32_t corrector;  /* -c, default 50   */
+    int32_t window;     /* -w, default 150  */
+    int32_t seg_dist;   /* -d, default 50   */
+    double std_scale;   /* -t, default 0.75 */
+    double stall_len;   /* -l, default 0.25 */
+    int32_t lim_lo;     /* -lim_low, default 0   */
+    int32_t lim_hi;     /* -lim_hi,  default 900 */
+    int32_t num;        /* -n: 0 = all (reference quirk: drops the last sample), >0 first n, <0 python slice */
+    int32_t max_segs;   /* capacity of segs per read */
+} sqk_seg_params;
+
+/* segs: [n_reads][max_segs][2] int32 (start, end); n_segs[n_reads]: segments found (0 == the
+ * reference's `False`); a count above max_segs means the row was truncated to max_segs. */
+SQK_API int sqk_segmenter(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                  int64_t max_read_len, const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
+
+/* ---------------------------------------------------------------------------------------
+ * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the
+ * launching stream around each launch.  Off by default.  Reading the counters synchronises.
+ * ------------------------------------------------------------------------------------- */
+enum sqk_kernel_id { SQK_K_STATS = 0, SQK_K_DTW = 1, SQK_K_SEG_FSM = 2, SQK_K_COUNT = 3 };
+typedef struct {
+    int64_t launches[SQK_K_COUNT];
+    double ms[SQK_K_COUNT];
+} sqk_timing;
+SQK_API int sqk_ctx_enable_timing(sqk_ctx *ctx, int on);
+SQK_API int sqk_ctx_get_timing(sqk_ctx *ctx, sqk_timing *out, int reset);
+
+/* Tuning knob for experiments: force lanes-per-read of the DTW kernel (0 = automatic). */
+SQK_API int sqk_ctx_set_dtw_lanes(sqk_ctx *ctx, int lanes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQK_H */

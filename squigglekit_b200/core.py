@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's per-read functions, batched over reads and executed by
+libsqk's sm_100a kernels through the C ABI (include/sqk.h).
+
+Reference call sites replaced:
+  * ``dtw_subsequence(model[name], sig)`` + the normalisation block in front of it
+    (MotifSeq.py:180-209, 437-439)  ->  :meth:`Context.motifseq`
+  * ``get_segs(sig, args)`` + ``sig[:Num]`` + ``scale_outliers`` (segmenter.py:124-128, 399-470)
+    ->  :meth:`Context.segmenter`;  ``test_segs`` (segmenter.py:473-494) -> :func:`test_segs`
+
+Inputs are either numpy arrays (host mode: the library streams them to the GPU in chunks) or
+torch CUDA tensors (device mode: kernels are enqueued on torch's current stream, nothing is
+copied).  torch is plumbing here -- device memory and streams -- not the compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import HIT_DTYPE, SqkError  # noqa: F401
+
+
+@dataclass
+class SegConfig:
+    """get_segs / test_segs parameters; defaults are the reference's argparse defaults
+    (segmenter.py:65-94)."""
+    error: int = 5
+    corrector: int = 50
+    window: int = 150
+    seg_dist: int = 50
+    std_scale: float = 0.75
+    stall_len: float = 0.25
+    lim_low: int = 0
+    lim_hi: int = 900
+    Num: int = 0
+    stall: bool = False
+    stall_start: int = 300
+    gap: bool = False
+    gap_dist: int = 3000
+    max_segs: int = 16
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by page-locked host memory (sqk_host_alloc); host-mode calls overlap
+    the H2D copy with compute only when the signal buffer is pinned."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _cabi.check(_cabi.lib().sqk_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = p.value
+    return arr
+
+
+_PINNED: dict[int, int] = {}
+
+
+def pinned_free(arr: np.ndarray) -> None:
+    addr = arr.__array_interface__["data"][0]
+    p = _PINNED.pop(addr, None)
+    if p is not None:
+        _cabi.check(_cabi.lib().sqk_host_free(p))
+
+
+class Context:
+    """One libsqk context = one GPU.  Not thread-safe (one per host thread)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _cabi.lib()
+        h = C.c_void_p()
+        _cabi.check(self._lib.sqk_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        props = (C.c_int64 * 5)()
+        _cabi.check(self._lib.sqk_ctx_device_props(self._h, props))
+        self.n_sms, self.smem_optin, self.clock_khz, self.l2_bytes, self.cc = (int(v) for v in props)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sqk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- instrumentation -----------------------------------------------------------------
+    def enable_timing(self, on: bool = True):
+        _cabi.check(self._lib.sqk_ctx_enable_timing(self._h, int(on)))
+
+    def timing(self, reset: bool = True) -> dict:
+        t = _cabi.Timing()
+        _cabi.check(self._lib.sqk_ctx_get_timing(self._h, C.byref(t), int(reset)))
+        names = ["stats", "dtw", "seg_fsm"]
+        return {n: {"launches": int(t.launches[i]), "ms": float(t.ms[i])} for i, n in enumerate(names)}
+
+    def set_dtw_lanes(self, lanes: int):
+        _cabi.check(self._lib.sqk_ctx_set_dtw_lanes(self._h, int(lanes)))
+
+    def sync(self):
+        _cabi.check(self._lib.sqk_ctx_sync(self._h))
+
+    def _use_torch_stream(self):
+        import torch
+        _cabi.check(self._lib.sqk_ctx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    # ---- MotifSeq ------------------------------------------------------------------------
+    @staticmethod
+    def _pack_models(models):
+        if isinstance(models, np.ndarray) and models.ndim == 1:
+            models = [models]
+        vecs = [np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in models]
+        if not vecs:
+            raise ValueError("no models")
+        offs = np.zeros(len(vecs) + 1, dtype=np.int32)
+        np.cumsum([v.size for v in vecs], out=offs[1:])
+        return np.concatenate(vecs), offs
+
+    def motifseq(self, signals, offsets, models, scale: str = "medmad", scale_low: int = 0, scale_hi: int = 1200,
+                 precision: str = "fp64", max_read_len: int = 0, out=None, want_kept: bool = True):
+        """Batched ``scale_outliers -> normalise -> dtw_subsequence`` (MotifSeq.py:180-209,437-439).
+
+        signals: int16 [total_samples]; offsets: int64 [n_reads+1]; models: one float64 vector or a list.
+        -> (hits, n_kept): hits is a structured array [n_reads, n_models] with fields start, end,
+        dist (host mode) or a uint8 CUDA tensor [n_reads, n_models, 16] holding the same records
+        (device mode; see :func:`hits_from_torch`).  start = -1: read empty after outlier removal;
+        -2: MAD == 0.
+        """
+        mvec, moffs = self._pack_models(models)
+        params = _cabi.MotifParams(_cabi.SCALE[scale], int(scale_low), int(scale_hi), _cabi.PRECISION[precision])
+        n_models = moffs.size - 1
+        if _is_torch(signals):
+            import torch
+            if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
+                raise TypeError("device mode needs int16 signals and int64 offsets")
+            if not (signals.is_cuda and offsets.is_cuda and signals.is_contiguous() and offsets.is_contiguous()):
+                raise ValueError("device mode needs contiguous CUDA tensors")
+            n_reads = offsets.numel() - 1
+            dev = signals.device
+            hits = out if out is not None else torch.empty((n_reads, n_models, 16), dtype=torch.uint8, device=dev)
+            kept = torch.empty(n_reads, dtype=torch.int32, device=dev) if want_kept else None
+            self._use_torch_stream()
+            _cabi.check(self._lib.sqk_motifseq(
+                self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, int(max_read_len), mvec.ctypes.data,
+                moffs.ctypes.data, n_models, C.byref(params), _cabi.SQK_MEM_DEVICE, hits.data_ptr(),
+                kept.data_ptr() if kept is not None else None))
+            return hits, kept
+        signals = np.ascontiguousarray(signals, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_reads = offsets.size - 1
+        hits = out if out is not None else np.zeros((n_reads, n_models), dtype=HIT_DTYPE)
+        kept = np.zeros(n_reads, dtype=np.int32) if want_kept else None
+        _cabi.check(self._lib.sqk_motifseq(
+            self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len), mvec.ctypes.data,
+            moffs.ctypes.data, n_models, C.byref(params), _cabi.SQK_MEM_HOST, hits.ctypes.data,
+            kept.ctypes.data if kept is not None else None))
+        return hits, kept
+
+    def motifseq_trace(self, signal, model, scale: str = "medmad", scale_low: int = 0, scale_hi: int = 1200,
+                       precision: str = "fp64"):
+        """One read, one model: -> (hit record, normalised signal, cost[-1, :]) -- what ``-x`` prints
+        (MotifSeq.py:447) and view_region plots (MotifSeq.py:507-509)."""
+        signal = np.ascontiguousarray(signal, dtype=np.int16)
+        model = np.ascontiguousarray(model, dtype=np.float64)
+        params = _cabi.MotifParams(_cabi.SCALE[scale], int(scale_low), int(scale_hi), _cabi.PRECISION[precision])
+        last = np.zeros(signal.size, dtype=np.float64)
+        norm = np.zeros(signal.size, dtype=np.float64)
+        hit = np.zeros(1, dtype=HIT_DTYPE)
+        n_out = C.c_int64(0)
+        _cabi.check(self._lib.sqk_motifseq_trace(self._h, signal.ctypes.data, signal.size, model.ctypes.data, model.size,
+                                                 C.byref(params), last.ctypes.data, norm.ctypes.data, signal.size,
+                                                 C.byref(n_out), hit.ctypes.data))
+        n = n_out.value
+        return hit[0], norm[:n], last[:n]
+
+    # ---- segmenter -----------------------------------------------------------------------
+    def segmenter(self, signals, offsets, cfg: SegConfig = SegConfig(), max_read_len: int = 0):
+        """Batched ``sig[:Num] -> scale_outliers -> get_segs`` (segmenter.py:124-128,399-470).
+
+        -> (segs int32 [n_reads, max_segs, 2], n_segs int32 [n_reads]); n_segs == 0 is the
+        reference's ``False``; n_segs > max_segs means the row was truncated (raise max_segs).
+        """
+        p = _cabi.SegParams(cfg.error, cfg.corrector, cfg.window, cfg.seg_dist, cfg.std_scale, cfg.stall_len,
+                            cfg.lim_low, cfg.lim_hi, cfg.Num, cfg.max_segs)
+        if _is_torch(signals):
+            import torch
+            if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
+                raise TypeError("device mode needs int16 signals and int64 offsets")
+            n_reads = offsets.numel() - 1
+            dev = signals.device
+            segs = torch.zeros((n_reads, cfg.max_segs, 2), dtype=torch.int32, device=dev)
+            nsegs = torch.zeros(n_reads, dtype=torch.int32, device=dev)
+            self._use_torch_stream()
+            _cabi.check(self._lib.sqk_segmenter(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads,
+                                                int(max_read_len), C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(),
+                                                nsegs.data_ptr()))
+            return segs, nsegs
+        signals = np.ascontiguousarray(signals, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_reads = offsets.size - 1
+        segs = np.zeros((n_reads, cfg.max_segs, 2), dtype=np.int32)
+        nsegs = np.zeros(n_reads, dtype=np.int32)
+        _cabi.check(self._lib.sqk_segmenter(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
+                                            C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
+        return segs, nsegs
+
+
+def hits_from_torch(hits_u8) -> np.ndarray:
+    """uint8 CUDA tensor [n, m, 16] of sqk_hit records -> structured numpy array [n, m]."""
+    a = hits_u8.cpu().numpy()
+    return a.reshape(a.shape[0], a.shape[1] * 16).view(HIT_DTYPE).reshape(a.shape[0], a.shape[1])
+
+
+def segs_to_lists(segs: np.ndarray, n_segs: np.ndarray):
+    """Batch output -> what get_segs returns per read: list of [start, end] or False."""
+    out = []
+    cap = segs.shape[1]
+    for r in range(n_segs.shape[0]):
+        n = int(n_segs[r])
+        if n > cap:
+            raise OverflowError(f"read {r}: {n} segments > max_segs={cap}")
+        out.append([[int(segs[r, i, 0]), int(segs[r, i, 1])] for i in range(n)] if n else False)
+    return out
+
+
+def test_segs(segs, cfg: SegConfig):
+    """segmenter.test_segs (segmenter.py:473-494): -k rejects reads whose first segment starts after
+    stall_start; -g rejects reads whose second segment starts more than gap_dist after the first ends
+    (a single-segment read passes, as the reference's swallowed IndexError makes it)."""
+    if not segs:
+        return False
+    if cfg.stall and segs[0][0] > cfg.stall_start:
+        return False
+    if cfg.gap and len(segs) > 1 and segs[1][0] > segs[0][1] + cfg.gap_dist:
+        return False
+    return segs
+
+
+test_segs.__test__ = False  # not a pytest test

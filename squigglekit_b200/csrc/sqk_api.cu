@@ -1,0 +1,793 @@
+// sqk_api.cu -- the C ABI of libsqk.so (include/sqk.h): context, scratch memory, the
+// host-buffer streaming pipeline and the device-buffer enqueue path around the three kernels
+// (sqk_stats.cuh, sqk_dtw.cuh, sqk_segmenter.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "sqk_dtw_launch.cuh"
+#include "sqk_segmenter.cuh"
+#include "sqk_stats.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? SQK_ERR_NOMEM : SQK_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+#define TRY(call)                  \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != SQK_OK) return rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+static int ensure(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SQK_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) { b.p = nullptr; return fail(SQK_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return SQK_OK;
+}
+
+static void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+struct HostBuf {              // pinned host staging
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+static int ensure_host(HostBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SQK_OK;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { b.p = nullptr; cudaGetLastError(); return fail(SQK_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return SQK_OK;
+}
+
+struct Pending { void *dst; const void *src; size_t bytes; };
+
+struct Slot {                 // everything one in-flight chunk needs
+    cudaStream_t stream = nullptr;
+    DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage;
+    HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
+    Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
+    int n_pend = 0;
+};
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// device -> caller's host array, without stalling the pipeline when that array is pageable
+static int result_to_host(Slot &s, int which, void *dst, const void *dev_src, size_t bytes, bool dst_pinned)
+{
+    if (bytes == 0) return SQK_OK;
+    if (dst_pinned) {
+        CU(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, s.stream));
+        return SQK_OK;
+    }
+    TRY(ensure_host(s.hout[which], bytes));
+    CU(cudaMemcpyAsync(s.hout[which].p, dev_src, bytes, cudaMemcpyDeviceToHost, s.stream));
+    s.pend[s.n_pend++] = Pending{dst, s.hout[which].p, bytes};
+    return SQK_OK;
+}
+
+static int recycle(Slot &s)   // wait for the slot's previous chunk and hand its results over
+{
+    CU(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < s.n_pend; i++) memcpy(s.pend[i].dst, s.pend[i].src, s.pend[i].bytes);
+    s.n_pend = 0;
+    return SQK_OK;
+}
+
+struct TimeRec { int kid; cudaEvent_t a, b; };
+
+struct sqk_ctx {
+    int device = 0;
+    int n_sms = 0;
+    int smem_optin = 0;
+    int clock_khz = 0;
+    int l2_bytes = 0;
+    int cc = 0;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    Slot slot[2];
+    DevBuf model;
+    DevBuf scratch8;
+    bool timing = false;
+    std::vector<TimeRec> recs;
+    std::vector<cudaEvent_t> pool;
+    sqk_timing acc{};
+    int force_lanes = 0;
+    int stats_smem_set = -1;
+};
+
+struct Guard {   // make the ctx device current for the duration of a call
+    int prev = -1;
+    bool ok = false;
+    explicit Guard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int tick(sqk_ctx *c, int kid, cudaStream_t st, cudaEvent_t *b_out)
+{
+    *b_out = nullptr;
+    if (!c->timing) return SQK_OK;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) {
+        if (!c->pool.empty()) { ev[i] = c->pool.back(); c->pool.pop_back(); }
+        else CU(cudaEventCreate(&ev[i]));
+    }
+    CU(cudaEventRecord(ev[0], st));
+    c->recs.push_back({kid, ev[0], ev[1]});
+    *b_out = ev[1];
+    return SQK_OK;
+}
+
+static int tock(cudaEvent_t b, cudaStream_t st)
+{
+    if (b) CU(cudaEventRecord(b, st));
+    return SQK_OK;
+}
+
+static int drain_timing(sqk_ctx *c)
+{
+    for (auto &r : c->recs) {
+        CU(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, r.a, r.b));
+        c->acc.launches[r.kid] += 1;
+        c->acc.ms[r.kid] += ms;
+        c->pool.push_back(r.a);
+        c->pool.push_back(r.b);
+    }
+    c->recs.clear();
+    return SQK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+__global__ void sqk_max_len_kernel(const int64_t *offsets, int64_t n_reads, unsigned long long *out)
+{
+    unsigned long long m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = offsets[i + 1] - offsets[i];
+        if (d > 0 && (unsigned long long)d > m) m = (unsigned long long)d;
+        if (d < 0) m = ~0ull;   // offsets not monotone
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(SQK_FULL_MASK, m, d);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Debug / plotting path (MotifSeq.py:447 `-x`, :507-509 cost[-1,]): one read, one CTA.  Writes the
+// normalised post-outlier signal and the whole last DTW row.  Row i is owned by thread i; columns
+// advance as an anti-diagonal through shared memory -- an implementation independent of
+// sqk_dtw_kernel, which the tests also use to cross-check it.
+__global__ void sqk_trace_normalise_kernel(const int16_t *sig, int64_t n, int lo, int hi, double center, double scale,
+                                           double *out, int *n_out)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n; b += blockDim.x) {
+        const int64_t i = b + tid;
+        const int v = i < n ? (int)sig[i] : 0;
+        const bool keep = i < n && v > lo && v < hi;
+        const unsigned bal = __ballot_sync(SQK_FULL_MASK, keep);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int pos = running + __popc(bal & ((1u << lane) - 1u));
+        int all = 0;
+        for (int w = 0; w < nw; w++) { if (w < warp) pos += warp_tot[w]; all += warp_tot[w]; }
+        if (keep) out[pos] = __ddiv_rn(__dsub_rn((double)v, center), scale);
+        __syncthreads();
+        if (tid == 0) running += all;
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = running;
+}
+
+__global__ void sqk_trace_lastrow_kernel(const double *y, int m, const double *x, int n, double *last_row)
+{
+    extern __shared__ double sh[];   // cur[n], prev1[n], prev2[n]: columns j, j-1 (per row, skewed)
+    double *col1 = sh, *col2 = sh + n;
+    const int i = threadIdx.x;
+    const double xi = i < n ? x[i] : 0.0;
+    double left = SQK_INF_D;         // C[i][j-1]
+    if (i < n) { col1[i] = SQK_INF_D; col2[i] = SQK_INF_D; }
+    __syncthreads();
+    for (int t = 0; t < m + n - 1; t++) {
+        const int j = t - i;
+        double nc = SQK_INF_D;
+        const bool on = (i < n && j >= 0 && j < m);
+        if (on) {
+            // col1[i-1] = C[i-1][j] (written by thread i-1 last step), col2[i-1] = C[i-1][j-1]
+            double best;
+            if (i == 0) best = 0.0;
+            else {
+                const double up = col1[i - 1], dg = col2[i - 1];
+                best = up;
+                if (dg < best) best = dg;
+                if (left < best) best = left;
+                if (j == 0) best = up;
+            }
+            nc = __dadd_rn(fabs(__dsub_rn(xi, y[j])), best);
+        }
+        __syncthreads();
+        if (on) {
+            col2[i] = col1[i];
+            col1[i] = nc;
+            left = nc;
+            if (i == n - 1) last_row[j] = nc;
+        } else if (i < n && j >= m) {
+            col2[i] = col1[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch plumbing shared by host and device mode
+// ------------------------------------------------------------------------------------------
+struct View {                 // a set of reads resident on the device
+    const int16_t *base;      // base[i] = absolute sample i
+    int64_t alloc_lo, alloc_hi;
+    const int64_t *offsets;   // indexable by absolute read id
+    int64_t read0;
+    int64_t n_reads;
+    int64_t max_len;
+};
+
+static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
+                        double std_scale, int32_t *d_nkept)
+{
+    TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
+    const int static_smem = (int)sizeof(StatsShared) + 64;
+    const int cap_max = (c->smem_optin - static_smem - 1024) / 2;
+    int64_t cap = std::min<int64_t>(std::max<int64_t>(v.max_len, 8), cap_max);
+    cap = (cap + 7) & ~7ll;
+    const int dyn = (int)cap * 2;
+    if (dyn > c->stats_smem_set) {
+        CU(cudaFuncSetAttribute(sqk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        c->stats_smem_set = dyn;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel, SQK_STATS_THREADS, dyn));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * per_sm));
+
+    StatsArgs a{};
+    a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+    a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = v.n_reads;
+    a.stats = (ReadStats *)s.stats.p; a.n_kept_out = d_nkept;
+    a.mode = mode; a.lo = lo; a.hi = hi; a.num = num; a.std_scale = std_scale;
+    a.cap = (int)cap; a.gstage = nullptr; a.gstage_stride = 0;
+    if (v.max_len > cap && mode != SQK_STATS_NONE) {
+        const int64_t stride = (v.max_len + 7) & ~7ll;
+        TRY(ensure(s.gstage, (size_t)grid * stride * sizeof(int16_t)));
+        a.gstage = (int16_t *)s.gstage.p; a.gstage_stride = stride;
+    }
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_STATS, st, &eb));
+    sqk_stats_kernel<<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_out, sqk_dtw_launcher *fn)
+{
+    static const int kmin[5] = {SQK_DTW_L1_KMIN, SQK_DTW_L4_KMIN, SQK_DTW_L8_KMIN, SQK_DTW_L16_KMIN, SQK_DTW_L32_KMIN};
+    static const int kmax[5] = {SQK_DTW_L1_KMAX, SQK_DTW_L4_KMAX, SQK_DTW_L8_KMAX, SQK_DTW_L16_KMAX, SQK_DTW_L32_KMAX};
+    static const int lanes[5] = {1, 4, 8, 16, 32};
+    static const sqk_dtw_launcher f64[5] = {sqk_launch_dtw_f64_l1, sqk_launch_dtw_f64_l4, sqk_launch_dtw_f64_l8,
+                                            sqk_launch_dtw_f64_l16, sqk_launch_dtw_f64_l32};
+    static const sqk_dtw_launcher f32[5] = {sqk_launch_dtw_f32_l1, sqk_launch_dtw_f32_l4, sqk_launch_dtw_f32_l8,
+                                            sqk_launch_dtw_f32_l16, sqk_launch_dtw_f32_l32};
+    auto fits = [&](int li) {
+        const int L = lanes[li], K = (N + L - 1) / L;
+        if (K < kmin[li] || K > kmax[li]) return false;
+        if (L * K - N > 0 && K < 2) return false;
+        return true;
+    };
+    int pick = -1;
+    if (c->force_lanes) {
+        for (int li = 0; li < 5; li++) if (lanes[li] == c->force_lanes && fits(li)) pick = li;
+        if (pick < 0) return fail(SQK_ERR_UNSUPPORTED, "motif of %d points cannot run with %d lanes per read", N, c->force_lanes);
+    } else {
+        // default policy: the fewest lanes whose rows-per-lane stays <= 20 (fewer shuffles per cell)
+        for (int li = 0; li < 5 && pick < 0; li++) if (fits(li)) pick = li;
+        if (pick < 0) return fail(SQK_ERR_UNSUPPORTED, "motif of %d points is longer than this build supports (max %d)", N,
+                                  32 * SQK_DTW_L32_KMAX);
+    }
+    *L_out = lanes[pick];
+    *K_out = (N + lanes[pick] - 1) / lanes[pick];
+    *fn = precision == SQK_PREC_FP32 ? f32[pick] : f64[pick];
+    return SQK_OK;
+}
+
+static int check_motif_params(const sqk_motif_params *p)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    if (p->scale_mode < 0 || p->scale_mode > 2) return fail(SQK_ERR_ARG, "scale_mode %d not in {0,1,2}", p->scale_mode);
+    if (p->precision < 0 || p->precision > 1) return fail(SQK_ERR_ARG, "precision %d not in {0,1}", p->precision);
+    return SQK_OK;
+}
+
+// stats + one DTW launch per model over a device-resident View; d_hits is [n_reads][n_models]
+static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
+                            const int32_t *h_model_offsets, int n_models, const sqk_motif_params *p, sqk_hit *d_hits,
+                            int32_t *d_nkept)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    TRY(launch_stats(c, s, st, v, p->scale_mode, p->lo, p->hi, 0, 0.0, d_nkept));
+    TRY(ensure(s.counter, 256 * sizeof(unsigned)));
+    if (n_models > 256) return fail(SQK_ERR_UNSUPPORTED, "more than 256 models per call");
+    CU(cudaMemsetAsync(s.counter.p, 0, 256 * sizeof(unsigned), st));
+    for (int m = 0; m < n_models; m++) {
+        const int N = h_model_offsets[m + 1] - h_model_offsets[m];
+        int L = 0, K = 0;
+        sqk_dtw_launcher fn = nullptr;
+        TRY(pick_dtw(c, N, p->precision, &L, &K, &fn));
+        DtwArgs a{};
+        a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+        a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+        a.stats = (const ReadStats *)s.stats.p;
+        a.model = d_models + h_model_offsets[m]; a.N = N;
+        a.lo = p->lo; a.hi = p->hi;
+        a.hits = d_hits + m; a.hit_stride = n_models;
+        a.counter = (unsigned *)s.counter.p + m;
+        cudaEvent_t eb;
+        TRY(tick(c, SQK_K_DTW, st, &eb));
+        cudaError_t e = fn(K, a, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        TRY(tock(eb, st));
+    }
+    return SQK_OK;
+}
+
+static int check_seg_params(const sqk_seg_params *p)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    if (p->max_segs < 1) return fail(SQK_ERR_ARG, "max_segs must be >= 1");
+    if (p->corrector < 0) return fail(SQK_ERR_ARG, "corrector must be >= 0");
+    if (p->window < 0 || p->error < 0) return fail(SQK_ERR_ARG, "window and error must be >= 0");
+    return SQK_OK;
+}
+
+static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const sqk_seg_params *p,
+                             int32_t *d_segs, int32_t *d_nsegs)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr));
+    FsmArgs a{};
+    a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+    a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+    a.stats = (const ReadStats *)s.stats.p;
+    a.lo = p->lim_lo; a.hi = p->lim_hi; a.num = p->num;
+    a.error = p->error; a.corrector = p->corrector; a.window = p->window; a.seg_dist = p->seg_dist;
+    const double fm = std::ceil((double)p->window * p->stall_len);
+    a.first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
+    a.max_segs = p->max_segs; a.segs = d_segs; a.n_segs = d_nsegs;
+    const unsigned grid = (unsigned)((v.n_reads + SQK_FSM_THREADS - 1) / SQK_FSM_THREADS);
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
+    sqk_fsm_kernel<<<grid, SQK_FSM_THREADS, 0, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+static int device_max_len(sqk_ctx *c, cudaStream_t st, const int64_t *d_offsets, int64_t n_reads, int64_t *out)
+{
+    TRY(ensure(c->scratch8, 8));
+    CU(cudaMemsetAsync(c->scratch8.p, 0, 8, st));
+    const int grid = (int)std::min<int64_t>(4 * c->n_sms, (n_reads + 255) / 256);
+    sqk_max_len_kernel<<<std::max(grid, 1), 256, 0, st>>>(d_offsets, n_reads, (unsigned long long *)c->scratch8.p);
+    CU(cudaGetLastError());
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, c->scratch8.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h == ~0ull) return fail(SQK_ERR_ARG, "offsets are not non-decreasing");
+    *out = (int64_t)h;
+    return SQK_OK;
+}
+
+// Split [0, n_reads) into chunks of about `target` samples (at least one read each).
+static void plan_chunks(const int64_t *offsets, int64_t n_reads, int64_t target, std::vector<int64_t> &cuts)
+{
+    cuts.clear();
+    cuts.push_back(0);
+    int64_t r = 0;
+    while (r < n_reads) {
+        int64_t e = r + 1;
+        const int64_t lim = offsets[r] + target;
+        // gallop + binary search for the last read ending within the target
+        int64_t lo = e, hi = n_reads;
+        while (lo < hi) {
+            const int64_t mid = lo + (hi - lo + 1) / 2;
+            if (offsets[mid] <= lim) lo = mid; else hi = mid - 1;
+        }
+        e = std::max(e, lo);
+        e = std::min(e, r + (int64_t)(1 << 22));   // bound reads per chunk (scratch sizes, int indices)
+        cuts.push_back(e);
+        r = e;
+    }
+}
+
+static const int64_t kChunkSamples = 24ll << 20;   // 48 MiB of int16 per in-flight chunk
+
+// ------------------------------------------------------------------------------------------
+// exported API
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int sqk_version(void) { return SQK_VERSION; }
+
+const char *sqk_last_error(void) { return g_err; }
+
+int sqk_device_count(int *count)
+{
+    if (!count) return fail(SQK_ERR_ARG, "count is NULL");
+    CU(cudaGetDeviceCount(count));
+    return SQK_OK;
+}
+
+int sqk_ctx_create(int device, sqk_ctx **out)
+{
+    if (!out) return fail(SQK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SQK_ERR_CUDA, "no CUDA device available (%s); libsqk has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(SQK_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    Guard g(device);
+    if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    sqk_ctx *c = new (std::nothrow) sqk_ctx();
+    if (!c) return fail(SQK_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    int v = 0;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); c->n_sms = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)); c->smem_optin = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); c->clock_khz = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device)); c->l2_bytes = v;
+    int maj = 0, min = 0;
+    CU(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, device));
+    c->cc = maj * 10 + min;
+    if (c->cc != 100) {
+        delete c;
+        return fail(SQK_ERR_UNSUPPORTED, "device %d is sm_%d; libsqk is built for sm_100a (B200) only", device, maj * 10 + min);
+    }
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+    *out = c;
+    return SQK_OK;
+}
+
+int sqk_ctx_destroy(sqk_ctx *c)
+{
+    if (!c) return SQK_OK;
+    Guard g(c->device);
+    cudaDeviceSynchronize();
+    for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto &e : c->pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        Slot &s = c->slot[i];
+        release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage);
+        for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    release(c->model); release(c->scratch8);
+    delete c;
+    return SQK_OK;
+}
+
+int sqk_ctx_set_stream(sqk_ctx *c, void *cuda_stream)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    c->user_stream = (cudaStream_t)cuda_stream;
+    c->use_user_stream = true;     // NULL is a valid stream (the legacy default stream)
+    return SQK_OK;
+}
+
+static cudaStream_t device_stream(sqk_ctx *c) { return c->use_user_stream ? c->user_stream : c->slot[0].stream; }
+
+int sqk_ctx_sync(sqk_ctx *c)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    Guard g(c->device);
+    CU(cudaStreamSynchronize(device_stream(c)));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    CU(cudaStreamSynchronize(c->slot[1].stream));
+    return SQK_OK;
+}
+
+int sqk_ctx_device_props(sqk_ctx *c, int64_t props[5])
+{
+    if (!c || !props) return fail(SQK_ERR_ARG, "NULL argument");
+    props[0] = c->n_sms; props[1] = c->smem_optin; props[2] = c->clock_khz; props[3] = c->l2_bytes; props[4] = c->cc;
+    return SQK_OK;
+}
+
+int sqk_host_alloc(uint64_t bytes, void **out)
+{
+    if (!out) return fail(SQK_ERR_ARG, "out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SQK_OK;
+}
+
+int sqk_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return SQK_OK;
+}
+
+int sqk_ctx_enable_timing(sqk_ctx *c, int on)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    c->timing = on != 0;
+    return SQK_OK;
+}
+
+int sqk_ctx_get_timing(sqk_ctx *c, sqk_timing *out, int reset)
+{
+    if (!c || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    Guard g(c->device);
+    TRY(drain_timing(c));
+    *out = c->acc;
+    if (reset) c->acc = sqk_timing{};
+    return SQK_OK;
+}
+
+int sqk_ctx_set_dtw_lanes(sqk_ctx *c, int lanes)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail(SQK_ERR_ARG, "lanes must be one of 0,1,4,8,16,32");
+    c->force_lanes = lanes;
+    return SQK_OK;
+}
+
+int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                 const double *models, const int32_t *model_offsets, int32_t n_models, const sqk_motif_params *p, int mem,
+                 sqk_hit *hits, int32_t *n_kept)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_reads < 0) return fail(SQK_ERR_ARG, "n_reads < 0");
+    if (n_reads == 0) return SQK_OK;
+    if (!offsets || !hits) return fail(SQK_ERR_ARG, "offsets/hits is NULL");
+    if (!models || !model_offsets || n_models < 1) return fail(SQK_ERR_ARG, "no models");
+    if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
+    TRY(check_motif_params(p));
+    for (int m = 0; m < n_models; m++)
+        if (model_offsets[m + 1] - model_offsets[m] < 1) return fail(SQK_ERR_ARG, "model %d is empty", m);
+    Guard g(c->device);
+    if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+
+    // models are tiny: always staged from the host copy (models / model_offsets are host pointers in both modes)
+    const size_t model_bytes = (size_t)model_offsets[n_models] * sizeof(double);
+    TRY(ensure(c->model, model_bytes));
+
+    if (mem == SQK_MEM_DEVICE) {
+        cudaStream_t st = device_stream(c);
+        if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, st));
+        if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
+        View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
+        // device mode: the caller's allocation bounds are unknown, so [offsets[0], offsets[n]) delimits what the
+        // kernels may touch (resolve_bounds): 16-byte blocks sticking out of it are read sample by sample.
+        TRY(enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, model_offsets, n_models, p, hits, n_kept));
+        return SQK_OK;
+    }
+
+    // ---- host mode: chunked, double-buffered H2D | stats+DTW | D2H ---------------------------
+    if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
+    int64_t maxlen = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t d = offsets[r + 1] - offsets[r];
+        if (d < 0) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
+        maxlen = std::max(maxlen, d);
+    }
+    if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
+    CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    std::vector<int64_t> cuts;
+    plan_chunks(offsets, n_reads, kChunkSamples, cuts);
+    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        Slot &s = c->slot[ci & 1];
+        cudaStream_t st = s.stream;
+        TRY(recycle(s));                 // the chunk that used this slot two iterations ago is done
+        const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], nr = r1 - r0;
+        const int64_t s0 = offsets[r0], s1 = offsets[r1], ns = s1 - s0;
+        TRY(ensure(s.signals, (size_t)std::max<int64_t>(ns, 8) * sizeof(int16_t) + 16));
+        TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
+        TRY(ensure(s.hits, (size_t)nr * n_models * sizeof(sqk_hit)));
+        TRY(ensure(s.nkept, (size_t)nr * sizeof(int32_t)));
+        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
+        TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
+                             (int32_t *)s.nkept.p));
+        TRY(result_to_host(s, 0, hits + r0 * n_models, s.hits.p, (size_t)nr * n_models * sizeof(sqk_hit), hits_pinned));
+        if (n_kept) TRY(result_to_host(s, 1, n_kept + r0, s.nkept.p, (size_t)nr * sizeof(int32_t), nkept_pinned));
+    }
+    TRY(recycle(c->slot[0]));
+    TRY(recycle(c->slot[1]));
+    return SQK_OK;
+}
+
+int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                  const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_reads < 0) return fail(SQK_ERR_ARG, "n_reads < 0");
+    if (n_reads == 0) return SQK_OK;
+    if (!offsets || !segs || !n_segs) return fail(SQK_ERR_ARG, "offsets/segs/n_segs is NULL");
+    if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
+    TRY(check_seg_params(p));
+    Guard g(c->device);
+    if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+    const size_t seg_row = (size_t)p->max_segs * 2 * sizeof(int32_t);
+
+    if (mem == SQK_MEM_DEVICE) {
+        cudaStream_t st = device_stream(c);
+        if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
+        View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
+        TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs));
+        return SQK_OK;
+    }
+
+    if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
+    int64_t maxlen = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t d = offsets[r + 1] - offsets[r];
+        if (d < 0) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
+        maxlen = std::max(maxlen, d);
+    }
+    if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
+    std::vector<int64_t> cuts;
+    plan_chunks(offsets, n_reads, kChunkSamples, cuts);
+    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        Slot &s = c->slot[ci & 1];
+        cudaStream_t st = s.stream;
+        TRY(recycle(s));
+        const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], nr = r1 - r0;
+        const int64_t s0 = offsets[r0], s1 = offsets[r1], ns = s1 - s0;
+        TRY(ensure(s.signals, (size_t)std::max<int64_t>(ns, 8) * sizeof(int16_t) + 16));
+        TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
+        TRY(ensure(s.segs, (size_t)nr * seg_row));
+        TRY(ensure(s.nsegs, (size_t)nr * sizeof(int32_t)));
+        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(s.segs.p, 0, (size_t)nr * seg_row, st));
+        View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
+        TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
+        TRY(result_to_host(s, 0, (char *)segs + (size_t)r0 * seg_row, s.segs.p, (size_t)nr * seg_row, segs_pinned));
+        TRY(result_to_host(s, 1, n_segs + r0, s.nsegs.p, (size_t)nr * sizeof(int32_t), nsegs_pinned));
+    }
+    TRY(recycle(c->slot[0]));
+    TRY(recycle(c->slot[1]));
+    return SQK_OK;
+}
+
+int sqk_motifseq_trace(sqk_ctx *c, const int16_t *signal, int64_t n_samples, const double *model, int32_t n_model,
+                       const sqk_motif_params *p, double *last_row, double *norm_sig, int64_t cap, int64_t *n_out,
+                       sqk_hit *hit)
+{
+    if (!c || !signal || !model || !n_out) return fail(SQK_ERR_ARG, "NULL argument");
+    if (n_samples < 1 || n_samples > 0x7fffffffLL) return fail(SQK_ERR_ARG, "n_samples out of range");
+    if (n_model < 1 || n_model > 1024) return fail(SQK_ERR_UNSUPPORTED, "trace supports motifs of 1..1024 points");
+    TRY(check_motif_params(p));
+    Guard g(c->device);
+    Slot &s = c->slot[0];
+    cudaStream_t st = s.stream;
+    CU(cudaStreamSynchronize(st));
+    const int64_t offs[2] = {0, n_samples};
+    TRY(ensure(s.signals, (size_t)n_samples * 2 + 16));
+    TRY(ensure(s.offsets, 2 * sizeof(int64_t)));
+    TRY(ensure(s.hits, sizeof(sqk_hit)));
+    TRY(ensure(s.nkept, sizeof(int32_t)));
+    TRY(ensure(c->model, (size_t)n_model * sizeof(double)));
+    CU(cudaMemcpyAsync(s.signals.p, signal, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->model.p, model, (size_t)n_model * sizeof(double), cudaMemcpyHostToDevice, st));
+    View v{(const int16_t *)s.signals.p, 0, n_samples, (const int64_t *)s.offsets.p, 0, 1, n_samples};
+    const int32_t mo[2] = {0, n_model};
+    TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, mo, 1, p, (sqk_hit *)s.hits.p, (int32_t *)s.nkept.p));
+    ReadStats rs;
+    sqk_hit h;
+    CU(cudaMemcpyAsync(&rs, s.stats.p, sizeof(rs), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h, s.hits.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hit) *hit = h;
+    *n_out = rs.n_kept;
+    if ((last_row || norm_sig) && rs.n_kept > 0 && !(rs.flags & SQK_FLAG_DEGENERATE)) {
+        if (cap < rs.n_kept) return fail(SQK_ERR_OVERFLOW, "cap %lld < %d kept samples", (long long)cap, rs.n_kept);
+        DevBuf ybuf, rowbuf, nbuf;
+        int rc = ensure(ybuf, (size_t)n_samples * sizeof(double));
+        if (rc == SQK_OK) rc = ensure(rowbuf, (size_t)n_samples * sizeof(double));
+        if (rc == SQK_OK) rc = ensure(nbuf, sizeof(int));
+        if (rc != SQK_OK) { release(ybuf); release(rowbuf); release(nbuf); return rc; }
+        sqk_trace_normalise_kernel<<<1, 256, 0, st>>>((const int16_t *)s.signals.p, n_samples, p->lo, p->hi, rs.center,
+                                                     rs.scale, (double *)ybuf.p, (int *)nbuf.p);
+        if (last_row) {
+            const int threads = ((n_model + 31) / 32) * 32;
+            sqk_trace_lastrow_kernel<<<1, threads, 2 * n_model * sizeof(double), st>>>(
+                (const double *)ybuf.p, rs.n_kept, (const double *)c->model.p, n_model, (double *)rowbuf.p);
+            cudaMemcpyAsync(last_row, rowbuf.p, (size_t)rs.n_kept * sizeof(double), cudaMemcpyDeviceToHost, st);
+        }
+        if (norm_sig) cudaMemcpyAsync(norm_sig, ybuf.p, (size_t)rs.n_kept * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        release(ybuf); release(rowbuf); release(nbuf);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "trace kernels: %s", cudaGetErrorString(e));
+    }
+    return SQK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// sqk_segmenter.cuh -- K3: segmenter.get_segs (segmenter.py:399-470) over many reads.
+//
+// The thresholds (median +- stdev*std_scale, segmenter.py:407-414) come from the stats kernel
+// (sqk_stats.cuh, SQK_STATS_SEGMENTER) already converted to the equivalent integer window
+// seg_lo <= x <= seg_hi.  What is left is the error-tolerant run-length state machine
+// (segmenter.py:420-464): inherently sequential per read, integer state.  One thread owns one
+// read and walks it with 16-byte loads (each lane streams its own cache line: sector-efficient,
+// L1 holds the 32 lines of a warp), dropping outliers on the fly so positions are in the
+// post-outlier index space exactly as in the reference; 32 reads advance per warp instruction.
+//
+// Kept quirks: `w` is never reset between segments; a segment still open at
+// the end of the read is not flushed; the first segment may be shorter (window*stall_len).
+#pragma once
+#include "sqk_common.cuh"
+
+#define SQK_FSM_THREADS 128
+
+struct FsmArgs {
+    const int16_t *base;
+    int64_t alloc_lo, alloc_hi;
+    const int64_t *offsets;
+    int64_t read0;
+    int n_reads;
+    const ReadStats *stats;
+    int lo, hi, num;
+    int error, corrector, window, seg_dist;
+    int first_min;            // ceil(window * stall_len): c >= window*stall_len  <=>  c >= first_min
+    int max_segs;
+    int32_t *segs;            // [n_reads][max_segs][2]
+    int32_t *n_segs;          // [n_reads]
+};
+
+__global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_reads) return;
+    int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
+    resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
+    const int64_t r = a.read0 + i;
+    const int64_t begin = a.offsets[r];
+    const int64_t end = begin + sqk_truncate_len(a.offsets[r + 1] - begin, a.num);
+    const ReadStats st = a.stats[i];
+    const int seg_lo = st.seg_lo, seg_hi = st.seg_hi;
+    int32_t *out = a.segs + (int64_t)i * a.max_segs * 2;
+
+    bool open = false;
+    int err = 0, run_err = 0, c = 0, w = a.corrector;
+    int start = 0, pos = 0, nseg = 0;
+    int last_start = 0, last_end = 0;
+
+    for (int64_t blk = aligned_block_start(a.base, begin); blk < end; blk += 8) {
+        const Samples8 smp = load_block8(a.base, blk, alloc_lo, alloc_hi);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int64_t idx = blk + e;
+            const int v = smp.get(e);
+            if (idx < begin || idx >= end || !(v > a.lo && v < a.hi)) continue;   // scale_outliers
+            if (v >= seg_lo && v <= seg_hi) {
+                if (!open) { start = pos; open = true; }
+                c++; w++;
+                run_err = 0;
+                if (c >= a.window && c >= w && (c % w) == 0) err--;
+            } else if (open) {
+                if (err < a.error) {
+                    c++; err++; run_err++;
+                    if (c >= a.window && c >= w && (c % w) == 0) err--;
+                } else {
+                    if (c >= a.window || (nseg == 0 && c >= a.first_min)) {
+                        const int stop = pos - run_err;
+                        if (nseg > 0 && start - last_end < a.seg_dist) {
+                            last_end = stop;
+                        } else {
+                            nseg++;
+                            last_start = start; last_end = stop;
+                        }
+                        if (nseg <= a.max_segs) { out[2 * (nseg - 1)] = last_start; out[2 * (nseg - 1) + 1] = last_end; }
+                    }
+                    open = false; c = 0; err = 0; run_err = 0;
+                }
+            }
+            pos++;
+        }
+    }
+    a.n_segs[i] = nseg;
+}

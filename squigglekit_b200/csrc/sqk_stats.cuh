@@ -1,0 +1,314 @@
+// sqk_stats.cuh -- K1: per-read outlier compaction + the statistics that normalisation
+// (MotifSeq.py:186-200) and get_segs (segmenter.py:407-414) need, bit-identical to numpy.
+//
+// One CTA per read (persistent, strided over reads).  The read is fetched from HBM ONCE with
+// 16-byte streaming loads, filtered  lo < s < hi  (scale_outliers, MotifSeq.py:317-324 /
+// segmenter.py:311-318) with a ballot-free popc prefix, and the survivors are parked as int16 in
+// shared memory (or, for reads longer than the shared-memory window, in a global scratch row);
+// every later pass runs from that copy.
+//
+//   zscale    mean = sum/n (integer sum: exact, order-free);  sd = sqrt(S/n) with S = the sum of
+//             fl(fl(x-mean)^2) taken in numpy's pairwise order (8-lane teams own the <=128-element
+//             leaves: one lane per strided accumulator, xor-butterfly = numpy's fold; the
+//             leaves are combined by a depth stack in DFS order) -> same bits as
+//             sklearn.preprocessing.scale / np.std.
+//   medmad    median and MAD by two-pass radix select on integer keys (x, then |2x - 2med|):
+//             exact, including the x.5 medians of even-length reads.
+//   segmenter median (select) + sd (pairwise) -> integer thresholds equivalent to bot < x < top.
+#pragma once
+#include "sqk_common.cuh"
+
+#define SQK_STATS_THREADS 128
+#define SQK_STATS_WARPS (SQK_STATS_THREADS / 32)
+#define SQK_STATS_TEAMS (SQK_STATS_THREADS / 8)
+#define SQK_LEAF_BATCH 64
+#define SQK_TREE_DEPTH 48
+#define SQK_HIST_BINS 512
+
+enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3 };
+
+struct StatsArgs {
+    const int16_t *base;      // base[i] = absolute sample i
+    int64_t alloc_lo, alloc_hi;
+    const int64_t *offsets;   // absolute sample offsets, [.. read0 + n_reads]
+    int64_t read0, n_reads;
+    ReadStats *stats;         // [n_reads], launch-local index
+    int32_t *n_kept_out;      // [n_reads] or null
+    int mode, lo, hi, num;
+    double std_scale;
+    int cap;                  // shared-memory staging capacity (samples)
+    int16_t *gstage;          // global staging rows for reads longer than cap (or null)
+    int64_t gstage_stride;
+};
+
+struct StatsShared {
+    unsigned long long sum_part[SQK_STATS_WARPS];
+    int warp_tot[SQK_STATS_WARPS];
+    uint32_t hist[SQK_HIST_BINS];
+    uint32_t sel[2];
+    int st_off[SQK_TREE_DEPTH], st_len[SQK_TREE_DEPTH], st_dep[SQK_TREE_DEPTH];
+    int lf_off[SQK_LEAF_BATCH], lf_len[SQK_LEAF_BATCH], lf_dep[SQK_LEAF_BATCH];
+    double lf_sum[SQK_LEAF_BATCH];
+    double cs_val[SQK_TREE_DEPTH];
+    int cs_dep[SQK_TREE_DEPTH];
+    int sp, csp, nleaf;
+    double result;
+};
+
+// numpy pairwise leaf (n <= 128) over sq[i] = fl(fl(x_i - mean)^2), evaluated by an 8-lane team.
+__device__ __forceinline__ double stats_leaf_sum(const int16_t *x, int off, int len, double mean, int k)
+{
+    if (len < 8) {
+        double r = 0.0;
+        for (int i = 0; i < len; i++) {
+            const double d = __dsub_rn((double)x[off + i], mean);
+            r = __dadd_rn(r, __dmul_rn(d, d));
+        }
+        return r;
+    }
+    const int body = len - (len & 7);
+    double d = __dsub_rn((double)x[off + k], mean);
+    double r = __dmul_rn(d, d);
+    for (int i = 8; i < body; i += 8) {
+        d = __dsub_rn((double)x[off + i + k], mean);
+        r = __dadd_rn(r, __dmul_rn(d, d));
+    }
+    r = __dadd_rn(r, shfl_xor_f64(r, 1, 8));   // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
+    r = __dadd_rn(r, shfl_xor_f64(r, 2, 8));   // ((r0+r1)+(r2+r3)) ...
+    r = __dadd_rn(r, shfl_xor_f64(r, 4, 8));
+    for (int i = body; i < len; i++) {
+        d = __dsub_rn((double)x[off + i], mean);
+        r = __dadd_rn(r, __dmul_rn(d, d));
+    }
+    return r;
+}
+
+// S = np.sum((x - mean)**2) for the n staged samples; result valid in every thread.
+__device__ double stats_pairwise_sq(const int16_t *x, int n, double mean, StatsShared &sh)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sh.st_off[0] = 0; sh.st_len[0] = n; sh.st_dep[0] = 0;
+        sh.sp = 1; sh.csp = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) {
+            // resume the depth-first walk: emit the next batch of leaves in numpy's evaluation order
+            int sp = sh.sp, nl = 0;
+            while (sp > 0 && nl < SQK_LEAF_BATCH) {
+                sp--;
+                const int off = sh.st_off[sp], len = sh.st_len[sp], dep = sh.st_dep[sp];
+                if (len <= 128) {
+                    sh.lf_off[nl] = off; sh.lf_len[nl] = len; sh.lf_dep[nl] = dep; nl++;
+                } else {
+                    int h = len / 2;
+                    h -= h % 8;
+                    sh.st_off[sp] = off + h; sh.st_len[sp] = len - h; sh.st_dep[sp] = dep + 1; sp++;   // right, popped later
+                    sh.st_off[sp] = off; sh.st_len[sp] = h; sh.st_dep[sp] = dep + 1; sp++;             // left, popped next
+                }
+            }
+            sh.sp = sp; sh.nleaf = nl;
+        }
+        __syncthreads();
+        const int nl = sh.nleaf;
+        if (nl == 0) break;
+        const int team = tid >> 3, k = tid & 7;
+        for (int q = team; q < ((nl + SQK_STATS_TEAMS - 1) / SQK_STATS_TEAMS) * SQK_STATS_TEAMS; q += SQK_STATS_TEAMS) {
+            // whole warps stay converged for the shuffles; surplus teams redo the last leaf
+            const int qq = q < nl ? q : nl - 1;
+            const double s = stats_leaf_sum(x, sh.lf_off[qq], sh.lf_len[qq], mean, k);
+            if (q < nl && k == 0) sh.lf_sum[q] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int csp = sh.csp;
+            for (int q = 0; q < nl; q++) {
+                double v = sh.lf_sum[q];
+                int dep = sh.lf_dep[q];
+                while (csp > 0 && sh.cs_dep[csp - 1] == dep) {   // sibling on the stack: left + right
+                    v = __dadd_rn(sh.cs_val[csp - 1], v);
+                    dep--; csp--;
+                }
+                sh.cs_val[csp] = v; sh.cs_dep[csp] = dep; csp++;
+            }
+            sh.csp = csp;
+            if (sh.sp == 0) sh.result = sh.cs_val[0];
+        }
+        __syncthreads();
+    }
+    return sh.result;
+}
+
+// rank-th smallest (0-based) of key(i), i < n, keys < 512*256.  Two-pass radix select.
+template <class KeyFn>
+__device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
+{
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        for (int b = tid; b < SQK_HIST_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += SQK_STATS_THREADS) {
+            const uint32_t kv = key(i);
+            if (pass == 0) atomicAdd(&sh.hist[kv >> 8], 1u);
+            else if ((kv >> 8) == prefix) atomicAdd(&sh.hist[kv & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int per = SQK_HIST_BINS / 32;
+            uint32_t mine = 0;
+            for (int b = 0; b < per; b++) mine += sh.hist[tid * per + b];
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
+                if (tid >= d) incl += t;
+            }
+            uint32_t cum = incl - mine;
+            if ((uint32_t)rank >= cum && (uint32_t)rank < incl) {
+                for (int b = 0; b < per; b++) {
+                    const uint32_t h = sh.hist[tid * per + b];
+                    if ((uint32_t)rank < cum + h) { sh.sel[0] = tid * per + b; sh.sel[1] = rank - cum; break; }
+                    cum += h;
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 0) { prefix = sh.sel[0]; rank = (int)sh.sel[1]; }
+        else prefix = (prefix << 8) | sh.sel[0];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const StatsArgs a)
+{
+    extern __shared__ __align__(16) int16_t smem_stage[];
+    __shared__ StatsShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
+    resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
+
+    for (int64_t i = blockIdx.x; i < a.n_reads; i += gridDim.x) {
+        const int64_t r = a.read0 + i;
+        const int64_t begin = a.offsets[r];
+        int64_t len = a.offsets[r + 1] - begin;
+        if (a.mode == SQK_STATS_SEGMENTER) len = sqk_truncate_len(len, a.num);
+        const int64_t end = begin + len;
+        const bool staged = (a.mode != SQK_STATS_NONE);
+        int16_t *stage = (len <= a.cap) ? smem_stage : a.gstage + (int64_t)blockIdx.x * a.gstage_stride;
+
+        // ---- pass over HBM: filter, compact, integer sum ------------------------------------
+        long long sum = 0;
+        int total = 0;
+        const int64_t blk0 = aligned_block_start(a.base, begin);
+        for (int64_t cb = blk0; cb < end; cb += SQK_STATS_THREADS * 8) {
+            const int64_t blk = cb + tid * 8;
+            Samples8 s;
+            unsigned keep = 0;
+            if (blk < end && blk + 8 > begin) {
+                s = load_block8(a.base, blk, alloc_lo, alloc_hi);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int v = s.get(e);
+                    const int64_t idx = blk + e;
+                    if (idx >= begin && idx < end && v > a.lo && v < a.hi) { keep |= 1u << e; sum += v; }
+                }
+            }
+            const int cnt = __popc(keep);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) sh.warp_tot[warp] = incl;
+            __syncthreads();
+            int pos = total + incl - cnt, all = 0;
+#pragma unroll
+            for (int w = 0; w < SQK_STATS_WARPS; w++) {
+                const int t = sh.warp_tot[w];
+                if (w < warp) pos += t;
+                all += t;
+            }
+            if (staged && keep) {
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+            }
+            total += all;
+            __syncthreads();
+        }
+        const int n = total;
+
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SQK_FULL_MASK, sum, d);
+        if (lane == 0) sh.sum_part[warp] = (unsigned long long)sum;
+        __syncthreads();
+        long long tot_sum = 0;
+#pragma unroll
+        for (int w = 0; w < SQK_STATS_WARPS; w++) tot_sum += (long long)sh.sum_part[w];
+        __syncthreads();   // staged samples visible to all; sum_part reusable
+
+        ReadStats out;
+        out.center = 0.0; out.scale = 1.0; out.n_kept = n; out.flags = 0; out.seg_lo = 0; out.seg_hi = -1;
+
+        if (n > 0 && (a.mode == SQK_STATS_ZSCALE || a.mode == SQK_STATS_SEGMENTER)) {
+            const double mean = __ddiv_rn((double)tot_sum, (double)n);
+            const double S = stats_pairwise_sq(stage, n, mean, sh);
+            double sd = __dsqrt_rn(__ddiv_rn(S, (double)n));
+            if (a.mode == SQK_STATS_ZSCALE) {
+                if (sd == 0.0) sd = 1.0;          // sklearn _handle_zeros_in_scale
+                out.center = mean; out.scale = sd;
+            } else {
+                out.scale = sd;                    // finished below once the median is known
+            }
+        }
+        if (n > 0 && (a.mode == SQK_STATS_MEDMAD || a.mode == SQK_STATS_SEGMENTER)) {
+            auto key_x = [stage](int q) -> uint32_t { return (uint32_t)((int)stage[q] + 32768); };
+            int med2;   // 2 * median, integer
+            if (n & 1) {
+                med2 = 2 * ((int)stats_select(key_x, n, (n - 1) / 2, sh) - 32768);
+            } else {
+                const int lo_v = (int)stats_select(key_x, n, n / 2 - 1, sh) - 32768;
+                const int hi_v = (int)stats_select(key_x, n, n / 2, sh) - 32768;
+                med2 = lo_v + hi_v;
+            }
+            const double median = (double)med2 * 0.5;
+            if (a.mode == SQK_STATS_MEDMAD) {
+                auto key_d = [stage, med2](int q) -> uint32_t {
+                    const int d = 2 * (int)stage[q] - med2;
+                    return (uint32_t)(d < 0 ? -d : d);
+                };
+                double mad;
+                if (n & 1) {
+                    mad = (double)stats_select(key_d, n, (n - 1) / 2, sh) * 0.5;
+                } else {
+                    const uint32_t d0 = stats_select(key_d, n, n / 2 - 1, sh);
+                    const uint32_t d1 = stats_select(key_d, n, n / 2, sh);
+                    mad = (double)(d0 + d1) * 0.25;
+                }
+                const double scaled = __dmul_rn(mad, 1.4826);
+                out.center = median; out.scale = scaled;
+                if (scaled == 0.0) out.flags |= SQK_FLAG_DEGENERATE;
+            } else {
+                const double spread = __dmul_rn(out.scale, a.std_scale);
+                const double top = __dadd_rn(median, spread);
+                const double bot = __dsub_rn(median, spread);
+                // integer x:  x < top  <=>  x <= ceil(top)-1 ;  x > bot  <=>  x >= floor(bot)+1
+                const double hi_d = fmin(fmax(ceil(top) - 1.0, -40000.0), 40000.0);
+                const double lo_d = fmin(fmax(floor(bot) + 1.0, -40000.0), 40000.0);
+                out.seg_hi = (top == top) ? (int)hi_d : -40000;   // NaN threshold: nothing is in range
+                out.seg_lo = (bot == bot) ? (int)lo_d : 40000;
+                out.center = top; out.scale = bot;
+            }
+        }
+        if (tid == 0) {
+            a.stats[i] = out;
+            if (a.n_kept_out) a.n_kept_out[i] = n;
+        }
+        __syncthreads();
+    }
+}
