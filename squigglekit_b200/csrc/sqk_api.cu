@@ -353,8 +353,14 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
         for (int li = 0; li < 5; li++) if (lanes[li] == c->force_lanes && fits(li)) pick = li;
         if (pick < 0) return fail(SQK_ERR_UNSUPPORTED, "motif of %d points cannot run with %d lanes per read", N, c->force_lanes);
     } else {
-        // default policy: the fewest lanes whose rows-per-lane stays <= 20 (fewer shuffles per cell)
-        for (int li = 0; li < 5 && pick < 0; li++) if (fits(li)) pick = li;
+        // default policy (measured on B200, profiles/): about 10 motif rows per lane keeps the kernel at
+        // <= 110 registers (4+ CTAs per SM) while one shuffle still pays for 10 cells; beyond 320 points
+        // every lane is in use and the rows per lane grow instead.
+        const int want_k = 10;
+        for (int li = 0; li < 5 && pick < 0; li++)
+            if (fits(li) && (N + lanes[li] - 1) / lanes[li] <= want_k) pick = li;
+        for (int li = 0; li < 5 && pick < 0; li++)
+            if (fits(li)) pick = li;
         if (pick < 0) return fail(SQK_ERR_UNSUPPORTED, "motif of %d points is longer than this build supports (max %d)", N,
                                   32 * SQK_DTW_L32_KMAX);
     }
@@ -475,7 +481,7 @@ static void plan_chunks(const int64_t *offsets, int64_t n_reads, int64_t target,
     }
 }
 
-static const int64_t kChunkSamples = 24ll << 20;   // 48 MiB of int16 per in-flight chunk
+static const int64_t kChunkSamples = 64ll << 20;   // 128 MiB of int16 per in-flight chunk: >= one full wave of CTAs at 4k samples/read
 
 // ------------------------------------------------------------------------------------------
 // exported API

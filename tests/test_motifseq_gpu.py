@@ -37,7 +37,9 @@ def test_golden_set(ctx, golden_dir, scale, mname):
     hits, kept = ctx.motifseq(g["signals"], g["offsets"], g["model_" + mname], scale=scale)
     key = f"{mname}_{scale}"
     want_start, want_end, want_dist = g[key + "_start"], g[key + "_end"], g[key + "_dist"]
-    pinned = want_start != -2           # the MAD == 0 read is a documented degenerate case
+    # reads whose MAD is 0 (constant / single-sample reads under medmad) have an all-NaN/inf normalised
+    # signal in the reference; libsqk reports status -2 for them instead of DTW-ing NaNs
+    pinned = (want_start != -2) & np.isfinite(want_dist)
     assert np.array_equal(hits["start"][pinned, 0], want_start[pinned])
     assert np.array_equal(hits["end"][pinned, 0], want_end[pinned])
     assert np.array_equal(hits["dist"][pinned, 0], want_dist[pinned])

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 def cfg_from(params: dict) -> sqk.SegConfig:
-    c = sqk.SegConfig(max_segs=64)
+    c = sqk.SegConfig(max_segs=512)
     for k, v in params.items():
         if k == "test":
             continue

@@ -1,0 +1,50 @@
+"""Summarise an .ncu-rep (read here, no GPU needed) into the handful of numbers DESIGN.md and
+bench.py quote.  usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/xxx.txt]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_static",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active",
+    "smsp__warps_eligible.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum", "sm__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print(f"== {name}  ({rep})")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:72s} {vals[i]:>18s} {units[i]}")
+        print("  -- warp stall reasons (pct of warp-active cycles per issue, > 1 %)")
+        st = []
+        for i, h in enumerate(hdr):
+            if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+                try:
+                    st.append((float(vals[i]), h))
+                except ValueError:
+                    pass
+        for v, h in sorted(st, reverse=True):
+            if v > 1.0:
+                print(f"  {h:92s} {v:8.2f}")
+
+
+if __name__ == "__main__":
+    main()
