@@ -1,0 +1,229 @@
+"""Drop-in command line for the reference's MotifSeq.py: same flags (MotifSeq.py:86-126), same stderr
+banner (:147-151), same TSV header and rows (:160-163, :446-449), same `.model` formats.  The per-read
+work (outlier removal, normalisation, subsequence DTW) runs in libsqk on the GPU, batched over reads;
+the experimental score columns (:441-445) are the same scipy/numpy expressions on the host.
+
+Deliberate differences, all loud:
+  * ``-m`` accepts the scrappie `.model` the reference ships (its own ``read_bait_model`` crashes on it and
+    never searches) as well as the bait format.
+  * ``-i`` (scrappie simulation of a fasta) needs the scrappie neural network: not available -> error.
+  * ``-v`` / ``--save`` plotting is out of scope -> warning, rows are still printed.
+  * reads that are empty after outlier removal, or whose MAD is 0 under medmad, are reported on stderr
+    and skipped (the reference raises / prints NaN rows for them).
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import os
+import sys
+
+import numpy as np
+
+VERSION = "1.3.0"
+BATCH_SAMPLES = 48 << 20
+BATCH_READS = 16384
+
+
+class MyParser(argparse.ArgumentParser):
+    def error(self, message):
+        sys.stderr.write('error: %s\n' % message)
+        self.print_help()
+        sys.exit(2)
+
+
+def build_parser():
+    parser = MyParser(description="MotifSeq - the Ctrl+f for signal. Signal-level local alignment of sequence motifs")
+    group = parser.add_mutually_exclusive_group()
+    mods = parser.add_mutually_exclusive_group()
+    group.add_argument("-f", "--f5f", help="File list of fast5 paths")
+    group.add_argument("-p", "--f5_path", help="Fast5 top dir")
+    group.add_argument("-s", "--signal", help="Extracted signal file from SquigglePull")
+    parser.add_argument("-l", "--scale", default="medmad", choices=["zscale", "medmad"],
+                        help="scaling/normalisation factor to use")
+    mods.add_argument("-i", "--fasta_input", help="fasta file to be converted to simulated signal by scrappy")
+    parser.add_argument("--scrappie_model", default="squiggle_r94",
+                        choices=['squiggle_r94', 'squiggle_r94_rna', 'squiggle_r10'],
+                        help="model to use with fasta_input for conversion")
+    mods.add_argument("-m", "--model",
+                      help="custom multiline .tsv of signal to search for - see docs - name{tab}60{tab}435...")
+    parser.add_argument("-x", "--sig_extract", action="store_true", help="Extract signal of match")
+    parser.add_argument("--slope", type=float, default=2.90, help="[Experimental] slope")
+    parser.add_argument("--intercept", type=float, default=-9.6, help="[Experimental] intercept")
+    parser.add_argument("--std_const", type=float, default=0.08468, help="[Experimental] standard deviation constant")
+    parser.add_argument("-v", "--view", action="store_true", help="view each output")
+    parser.add_argument("--save", help="save path for images")
+    parser.add_argument("--img", default="png", help="Type of image to save. png, jpeg, pdf, svg, etc. (default: png)")
+    parser.add_argument("-scale_hi", "--scale_hi", type=int, default=1200, help="Upper limit for signal outlier scaling")
+    parser.add_argument("-scale_low", "--scale_low", type=int, default=0, help="Lower limit for signal outlier scaling")
+    parser.add_argument("-V", "--version", action="store_true", help="Print version information")
+    parser.add_argument("--verbose", action="store_true", help="engage higher level of verbosity for troubleshooting")
+    # additions (not in the reference)
+    parser.add_argument("--device", type=int, default=0, help="[sqk] CUDA device index")
+    parser.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                        help="[sqk] fp64 = bit-exact with the reference's float64 DTW (default); fp32 = fast mode")
+    parser.add_argument("--start_col", type=int, default=8, help="[sqk] first signal column of a -s file (reference: 8)")
+    return parser
+
+
+def format_row(fast5, read_id, name, start, end, dist, m, b, std, L, extract=None):
+    """The row get_region_multi prints (MotifSeq.py:441-449), same expressions, same formatting."""
+    import scipy.stats as st
+    mod_mean = (m * L) + b
+    mod_stdev = mod_mean * std
+    Z = (dist - mod_mean) / mod_stdev
+    p_value = st.norm.cdf(Z)
+    hit_P = (1 - p_value) * 100
+    cols = [fast5, read_id, name, start, end, end - start, dist, mod_mean, mod_stdev, Z, p_value, hit_P]
+    if extract is not None:
+        cols.append('\t'.join([str(i) for i in extract]))
+    return "\t".join("{}".format(c) for c in cols)
+
+
+def _opener(path):
+    return gzip.open if path.endswith('.gz') else open
+
+
+def iter_reads(args):
+    """Yield (fast5_name, read_id, int16 signal) in the reference's iteration order."""
+    from . import fast5 as f5
+    if args.f5f:
+        with _opener(args.f5f)(args.f5f, 'rt') as s:
+            for l in s:
+                path = l.strip('\n').split('\t')[0]
+                if not path:
+                    continue
+                yield from _one_fast5(f5, path, path.split('/')[-1], "Failed to extract signal: {} {}\n".format(path, path.split('/')[-1]))
+    elif args.f5_path:
+        for dirpath, dirnames, files in os.walk(args.f5_path):
+            for fast5 in files:
+                if fast5.endswith('.fast5'):
+                    fast5_file = os.path.join(dirpath, fast5)
+                    yield from _one_fast5(f5, fast5_file, fast5,
+                                          "main():data not extracted. Moving to next file - {}\n".format(fast5_file))
+    elif args.signal:
+        with _opener(args.signal)(args.signal, 'rt') as s:
+            for l in s:
+                l = l.strip('\n').split('\t')
+                if len(l) <= args.start_col:
+                    sys.stderr.write("No Signal found - please check signal format\n")
+                    continue
+                vals = np.array([float(i) for i in l[args.start_col:]])
+                if not vals.any():
+                    sys.stderr.write("No Signal found - please check signal format\n")
+                    continue
+                ints = np.rint(vals)
+                if not np.array_equal(ints, vals) or ints.min() < -32768 or ints.max() > 32767:
+                    sys.stderr.write("{}: non-integer (pA) signal is not supported by the GPU path; extract raw "
+                                     "signal with SquigglePull -r\n".format(l[0]))
+                    continue
+                yield l[0], l[1], ints.astype(np.int16)
+
+
+def _one_fast5(f5, path, name, fail_msg):
+    try:
+        f = f5.Fast5File(path)
+        if f5.is_multi_fast5(f):
+            for rname, rec in f5.read_multi_fast5(path).items():
+                yield name, rec["read_id"], rec["signal"]
+        else:
+            rec = f5.read_single_fast5(path)
+            # h5py hands the reference a bytes object for fixed-length string attributes and it prints b'...'
+            # (MotifSeq.py:346, TODO at :46); reproduce that so downstream parsers see the same column
+            rid = "b'{}'".format(rec["read_id"]) if rec.get("read_id_is_bytes") else rec["read_id"]
+            yield name, rid, rec["signal"]
+    except Exception as e:          # the reference prints a traceback and moves on (MotifSeq.py:334-351)
+        sys.stderr.write("process_fast5():failed to extract events or fastq from: {} ({}: {})\n".format(path, type(e).__name__, e))
+        sys.stderr.write(fail_msg)
+
+
+def flush(ctx, args, batch, model, m_order, L, out):
+    if not batch:
+        return
+    sigs = [b[2] for b in batch]
+    offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
+    np.cumsum([s.size for s in sigs], out=offsets[1:])
+    signals = np.concatenate(sigs) if sigs else np.zeros(0, dtype=np.int16)
+    hits, kept = ctx.motifseq(signals, offsets, [model[n] for n in m_order], scale=args.scale,
+                              scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision)
+    for r, (fast5, read_id, sig) in enumerate(batch):
+        for c, name in enumerate(m_order):
+            h = hits[r, c]
+            start, end, dist = int(h["start"]), int(h["end"]), h["dist"]
+            if start < 0:
+                why = "no samples left after outlier removal" if start == -1 else "MAD is 0: med-MAD scaling undefined"
+                sys.stderr.write("{} {}: {} - skipped\n".format(fast5, read_id, why))
+                continue
+            extract = None
+            if args.sig_extract:
+                _, norm, _ = ctx.motifseq_trace(sig, model[name], scale=args.scale, scale_low=args.scale_low,
+                                                scale_hi=args.scale_hi, precision=args.precision)
+                extract = norm[start:end]
+            out.write(format_row(fast5, read_id, name, start, end, dist, args.slope, args.intercept, args.std_const,
+                                 L[c], extract) + "\n")
+    batch.clear()
+
+
+def main(argv=None):
+    parser = build_parser()
+    raw_args = sys.argv[1:] if argv is None else list(argv)
+    args = parser.parse_args(raw_args)
+    if not raw_args:
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+    if args.version:
+        sys.stderr.write("SquiggleKit MotifSeq: {}\n".format(VERSION))
+        sys.exit(1)
+    if args.verbose:
+        sys.stderr.write("Verbose mode active - dumping info to stderr\n")
+        sys.stderr.write("SquiggleKit MotifSeq: {}\n".format(VERSION))
+        sys.stderr.write("args: {}\n".format(args))
+
+    sys.stderr.write("\n\n**********************************************************\n")
+    sys.stderr.write("*  z-score, p-value, probability, etc. are based on      *\n")
+    sys.stderr.write("*     preliminary experimental modeling only             *\n")
+    sys.stderr.write("*                Use at own risk                         *\n")
+    sys.stderr.write("**********************************************************\n\n\n")
+
+    if args.fasta_input:
+        sys.stderr.write("-i/--fasta_input needs the scrappie neural-network simulator, which is not available here; "
+                         "run `scrappie squiggle` yourself and pass its output with -m\n")
+        sys.exit(1)
+    if not args.model:
+        sys.stderr.write("no model given (-m)\n")
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+    if args.view or args.save:
+        sys.stderr.write("warning: -v/--view and --save plotting are not part of the GPU port; printing rows only\n")
+    if not (args.f5f or args.f5_path or args.signal):
+        sys.stderr.write("Unknown file or path input")
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+
+    from . import Context, read_model
+    model, m_order, L = read_model(args.model)
+    if not m_order:
+        sys.stderr.write("no motif found in {}\n".format(args.model))
+        sys.exit(1)
+
+    out = sys.stdout
+    head = ["fast5", "readID", "model", "start", "end", "length", "distance_score", "model_mean", "model_stdev", "Z-score",
+            "p-value", "hit_Probability"]
+    if args.sig_extract:
+        head.append("normalised_signal")
+    out.write("\t".join(head) + "\n")
+
+    with Context(args.device) as ctx:
+        batch, n_samples = [], 0
+        for rec in iter_reads(args):
+            batch.append(rec)
+            n_samples += rec[2].size
+            if n_samples >= BATCH_SAMPLES or len(batch) >= BATCH_READS:
+                flush(ctx, args, batch, model, m_order, L, out)
+                n_samples = 0
+        flush(ctx, args, batch, model, m_order, L, out)
+    out.flush()
+
+
+if __name__ == '__main__':
+    main()

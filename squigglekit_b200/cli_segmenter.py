@@ -1,0 +1,184 @@
+"""Drop-in command line for the reference's segmenter.py: same flags (segmenter.py:53-97), same
+``name<TAB>s1,e1,s2,e2,...`` output (:138-143), same stderr messages.  Per read, the truncation
+``sig[:Num]`` (with the reference's Num=0 -> -1 quirk that drops the last sample, :104-105), the outlier
+removal (:311-318) and get_segs (:399-470) run in libsqk on the GPU, batched; test_segs (:473-494) is the
+same two comparisons on the host.
+
+Deliberate differences, all loud:
+  * fast5 input is segmented on the RAW integer signal (the reference's ``--raw_signal`` behaviour).  The
+    reference's default converts to pA rounded to 2 decimals first (:345-349), which moves the thresholds
+    by a fraction of a sample; float-signal kernels are listed as "next" in DESIGN.md.  Without
+    ``--raw_signal`` a note is written to stderr once.
+  * ``-s`` files with float columns are rejected per read (same reason).
+  * ``-v`` plotting is out of scope -> warning.
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import os
+import sys
+
+import numpy as np
+
+BATCH_SAMPLES = 48 << 20
+BATCH_READS = 16384
+
+
+class MyParser(argparse.ArgumentParser):
+    def error(self, message):
+        sys.stderr.write('error: %s\n' % message)
+        self.print_help()
+        sys.exit(2)
+
+
+def build_parser():
+    parser = MyParser(description="segmenter - script to find obvious regions in squiggle data")
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument("-i", "--ind", nargs='+', help="Individual fast5 file/s")
+    group.add_argument("-p", "--f5_path", help="Fast5 top dir")
+    group.add_argument("-s", "--signal", help="Extracted signal file from squigglePull")
+    parser.add_argument("--single", action="store_true", help="single fast5 files")
+    parser.add_argument("-n", "--Num", type=int, default=0, help="Section of signal to look at - default 0=all")
+    parser.add_argument("-e", "--error", type=int, default=5, help="Allowable error in segment algorithm")
+    parser.add_argument("-c", "--corrector", type=int, default=50,
+                        help="Window size for increasing total error correction - better long segment detection")
+    parser.add_argument("-w", "--window", type=int, default=150, help="Minimum segment window size to be detected")
+    parser.add_argument("-d", "--seg_dist", type=int, default=50, help="Maximum distance between 2 segments to be merged into 1")
+    parser.add_argument("-t", "--std_scale", type=float, default=0.75, help="Scale factor of STDev about median")
+    parser.add_argument("-v", "--view", action="store_true", help="view each output")
+    parser.add_argument("-g", "--gap", action="store_true", help="Turn on gap distance for stall to polyTAil")
+    parser.add_argument("-b", "--gap_dist", type=int, default=3000,
+                        help="Maximum distance between stall and polyTAil segment - for 10X/dRNA")
+    parser.add_argument("-k", "--stall", action="store_true", help="Turn on stall detection - must be present")
+    parser.add_argument("-u", "--test", action="store_true", help="Run Tests")
+    parser.add_argument("-l", "--stall_len", type=float, default=0.25,
+                        help="Minimum percentage of minimum window segment for initial stall segment")
+    parser.add_argument("-j", "--stall_start", type=int, default=300,
+                        help="Maximum distance for start of stall segment to be detected")
+    parser.add_argument("-lim_hi", "--lim_hi", type=int, default=900, help="Upper limit for signal outlier scaling")
+    parser.add_argument("-lim_low", "--lim_low", type=int, default=0, help="Lower limit for signal outlier scaling")
+    parser.add_argument("--raw_signal", action="store_true", help="Plot raw signal instead of converting to pA")
+    # additions (not in the reference)
+    parser.add_argument("--device", type=int, default=0, help="[sqk] CUDA device index")
+    parser.add_argument("--max_segs", type=int, default=64, help="[sqk] capacity of the per-read segment list")
+    parser.add_argument("--start_col", type=int, default=4, help="[sqk] first signal column of a -s file (reference: 4)")
+    return parser
+
+
+def _opener(path):
+    return gzip.open if path.endswith('.gz') else open
+
+
+def _fast5_reads(args, path, label):
+    """Yield (name_to_print, int16 signal) the way the reference's branches do: multi-read files print the
+    read group name (segmenter.py:143), single-read files print the file name (:174 / :288)."""
+    from . import fast5 as f5
+    try:
+        if not args.single:
+            for rname, rec in f5.read_multi_fast5(path).items():
+                yield rname, rec["signal"]
+        else:
+            yield label, f5.read_single_fast5(path)["signal"]
+    except Exception as e:
+        sys.stderr.write('process_fast5():failed to extract events or fastq from: {} ({}: {})'.format(path, type(e).__name__, e))
+        sys.stderr.write("main():data not extracted. Moving to next file: {}".format(label))
+
+
+def iter_reads(args):
+    if args.f5_path:
+        for dirpath, dirnames, files in os.walk(args.f5_path):
+            for fast5 in files:
+                if fast5.endswith('.fast5'):
+                    yield from _fast5_reads(args, os.path.join(dirpath, fast5), fast5)
+    elif args.ind:
+        for fast5_file in args.ind:
+            yield from _fast5_reads(args, fast5_file, fast5_file)
+    elif args.signal:
+        with _opener(args.signal)(args.signal, 'rt') as s:
+            for l in s:
+                l = l.strip('\n').split('\t')
+                fast5 = l[0]
+                if len(l) <= args.start_col:
+                    sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
+                    continue
+                if "." in l[args.start_col]:
+                    sys.stderr.write("{}: float (pA) signal is not supported by the GPU path; extract raw signal with "
+                                     "SquigglePull -r\n".format(fast5))
+                    continue
+                sig = np.array([int(i) for i in l[args.start_col:]], dtype=np.int64)
+                if not sig.any():
+                    sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
+                    continue
+                if sig.min() < -32768 or sig.max() > 32767:
+                    sys.stderr.write("{}: samples outside the int16 range\n".format(fast5))
+                    continue
+                yield fast5, sig.astype(np.int16)
+
+
+def flush(ctx, args, cfg, batch, out):
+    from . import segs_to_lists, test_segs
+    if not batch:
+        return
+    sigs = [b[1] for b in batch]
+    offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
+    np.cumsum([s.size for s in sigs], out=offsets[1:])
+    segs, nsegs = ctx.segmenter(np.concatenate(sigs), offsets, cfg)
+    for (name, _), found in zip(batch, segs_to_lists(segs, nsegs)):
+        if not found:
+            sys.stderr.write("no segments found: {}".format(name))
+            continue
+        if args.test:
+            if args.stall and found[0][0] > args.stall_start:
+                sys.stderr.write("start seg too late!")
+            elif args.gap and len(found) > 1 and found[1][0] > found[0][1] + args.gap_dist:
+                sys.stderr.write("second seg too far!")
+            found = test_segs(found, cfg)
+            if not found:
+                continue
+        flat = []
+        for i, j in found:
+            flat.append(str(i))
+            flat.append(str(j))
+        out.write("\t".join([name, ",".join(flat)]) + "\n")
+    batch.clear()
+
+
+def main(argv=None):
+    parser = build_parser()
+    raw_args = sys.argv[1:] if argv is None else list(argv)
+    args = parser.parse_args(raw_args)
+    if not raw_args:
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+    if not (args.f5_path or args.ind or args.signal):
+        sys.stderr.write("Unknown file or path input")
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+    if args.view:
+        sys.stderr.write("warning: -v/--view plotting is not part of the GPU port; printing segments only\n")
+    if (args.f5_path or args.ind) and not args.raw_signal:
+        sys.stderr.write("note: segmenting the raw integer signal (as with --raw_signal); pA conversion before "
+                         "segmentation is not implemented in the GPU path\n")
+
+    from . import Context, SegConfig
+    cfg = SegConfig(error=args.error, corrector=args.corrector, window=args.window, seg_dist=args.seg_dist,
+                    std_scale=args.std_scale, stall_len=args.stall_len, lim_low=args.lim_low, lim_hi=args.lim_hi,
+                    Num=args.Num, stall=args.stall, stall_start=args.stall_start, gap=args.gap, gap_dist=args.gap_dist,
+                    max_segs=args.max_segs)
+    out = sys.stdout
+    with Context(args.device) as ctx:
+        batch, n_samples = [], 0
+        for rec in iter_reads(args):
+            batch.append(rec)
+            n_samples += rec[1].size
+            if n_samples >= BATCH_SAMPLES or len(batch) >= BATCH_READS:
+                flush(ctx, args, cfg, batch, out)
+                n_samples = 0
+        flush(ctx, args, cfg, batch, out)
+    out.flush()
+    sys.stderr.write("Done")
+
+
+if __name__ == '__main__':
+    main()

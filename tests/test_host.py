@@ -1,0 +1,92 @@
+"""CPU tests of the host-side mirror of the reference interface: model files, fast5 extraction,
+test_segs, TSV row formatting, CLI flag surface."""
+import io
+import json
+import os
+
+import numpy as np
+
+import squigglekit_b200 as sqk
+from squigglekit_b200 import cli_motifseq, cli_segmenter, fast5
+
+
+def test_read_synth_model_matches_reference_output(golden_dir, tmp_path):
+    exp = json.load(open(os.path.join(golden_dir, "example_expected.json")))
+    ex = np.load(os.path.join(golden_dir, "example_read.npz"), allow_pickle=True)
+    p = tmp_path / "m.model"
+    p.write_text(exp["model_text"])
+    for reader in (sqk.read_synth_model, sqk.read_model):
+        model, order, L = reader(str(p))
+        assert order == ["3_prime_end"] and L == [20]
+        assert np.array_equal(model["3_prime_end"], ex["model"])
+
+
+def test_read_synth_model_multiple_blocks(tmp_path):
+    p = tmp_path / "two.model"
+    p.write_text("#a\npos\tbase\tcurrent\tsd\tdwell\n0\tA\t0.5\t0.1\t2.4\n1\tC\t-1.0\t0.1\t1.5\n#b\n0\tG\t2.0\t0.2\t3.0\n")
+    model, order, L = sqk.read_synth_model(str(p))
+    assert order == ["a", "b"] and L == [2, 1]
+    assert model["a"].tolist() == [0.5, 0.5, -1.0, -1.0] and model["b"].tolist() == [2.0, 2.0, 2.0]
+
+
+def test_read_bait_model_fills_order_and_lengths(tmp_path):
+    p = tmp_path / "bait.tsv"
+    p.write_text("adapter\t12\tx\t1.0\t2.0\t3.5\npolyA\t8\tx\t-0.5\t0.25\n")
+    model, order, L = sqk.read_model(str(p))
+    assert order == ["adapter", "polyA"] and L == [12, 8]
+    assert model["adapter"].tolist() == [1.0, 2.0, 3.5]
+
+
+def test_fast5_reader_on_the_reference_example(golden_dir):
+    rec = fast5.read_single_fast5(os.path.join(golden_dir, "test.fast5"))
+    ex = np.load(os.path.join(golden_dir, "example_read.npz"), allow_pickle=True)
+    assert rec["signal"].dtype == np.int16 and np.array_equal(rec["signal"], ex["raw"])
+    assert rec["read_id"] == str(ex["read_id"])
+    assert (rec["digitisation"], rec["offset"], rec["sampling_rate"]) == (8192.0, 16.0, 4000.0)
+    assert float("{0:.2f}".format(rec["range"])) == 1493.94
+    f = fast5.Fast5File(os.path.join(golden_dir, "test.fast5"))
+    assert sorted(f.keys()) == ["Analyses", "Raw", "UniqueGlobalKey"]
+    assert not fast5.is_multi_fast5(f)
+
+
+def test_test_segs_semantics():
+    cfg = sqk.SegConfig(stall=True, stall_start=300, gap=True, gap_dist=100)
+    assert sqk.test_segs([[10, 200], [250, 500]], cfg) == [[10, 200], [250, 500]]
+    assert sqk.test_segs([[301, 600]], cfg) is False                      # first segment starts too late
+    assert sqk.test_segs([[10, 200], [301, 500]], cfg) is False           # second segment too far
+    assert sqk.test_segs([[10, 200]], cfg) == [[10, 200]]                 # single segment: IndexError swallowed upstream
+    assert sqk.test_segs(False, cfg) is False
+
+
+def test_row_formatting_matches_reference_rows(golden_dir):
+    """format_row reproduces the TSV rows the reference's get_region_multi printed (golden), given the
+    same start/end/dist."""
+    exp = json.load(open(os.path.join(golden_dir, "example_expected.json")))
+    for scale in ("zscale", "medmad"):
+        want = exp["tsv"][scale].rstrip("\n")
+        f = want.split("\t")
+        row = cli_motifseq.format_row(f[0], f[1], f[2], int(f[3]), int(f[4]), np.float64(float(f[6])), 2.90, -9.6, 0.08468, 20)
+        assert row == want
+    rows = json.load(open(os.path.join(golden_dir, "motifseq_rows.json")))
+    g = np.load(os.path.join(golden_dir, "motifseq_golden.npz"))
+    for key, L in (("motif80_zscale", 10), ("example163_medmad", 20)):
+        lines = rows[key].rstrip("\n").split("\n")
+        for line in lines[:5]:
+            f = line.split("\t")
+            assert cli_motifseq.format_row(f[0], f[1], f[2], int(f[3]), int(f[4]), np.float64(float(f[6])), 2.90, -9.6, 0.08468, L) == line
+
+
+def test_cli_flag_surface_matches_reference():
+    ms = {a.dest for a in cli_motifseq.build_parser()._actions}
+    for flag in ("f5f", "f5_path", "signal", "scale", "fasta_input", "scrappie_model", "model", "sig_extract", "slope",
+                 "intercept", "std_const", "view", "save", "img", "scale_hi", "scale_low", "version", "verbose"):
+        assert flag in ms, flag
+    sg = {a.dest for a in cli_segmenter.build_parser()._actions}
+    for flag in ("ind", "f5_path", "signal", "single", "Num", "error", "corrector", "window", "seg_dist", "std_scale", "view",
+                 "gap", "gap_dist", "stall", "test", "stall_len", "stall_start", "lim_hi", "lim_low", "raw_signal"):
+        assert flag in sg, flag
+    d = cli_segmenter.build_parser().parse_args(["-s", "x"])
+    assert (d.error, d.corrector, d.window, d.seg_dist, d.std_scale, d.stall_len, d.stall_start, d.gap_dist, d.lim_hi, d.lim_low) == \
+        (5, 50, 150, 50, 0.75, 0.25, 300, 3000, 900, 0)
+    m = cli_motifseq.build_parser().parse_args(["-s", "x", "-m", "y"])
+    assert (m.scale, m.slope, m.intercept, m.std_const, m.scale_hi, m.scale_low) == ("medmad", 2.90, -9.6, 0.08468, 1200, 0)
