@@ -29,6 +29,11 @@
 
 #define SQK_DTW_WARPS 4
 #define SQK_DTW_THREADS (SQK_DTW_WARPS * 32)
+// resident CTAs per SM the register allocator must allow for (experiments: -DSQK_DTW_MINB_SMALLK=5)
+#ifndef SQK_DTW_MINB_SMALLK
+#define SQK_DTW_MINB_SMALLK 1
+#endif
+#define SQK_DTW_MINB(K) ((K) <= 10 ? SQK_DTW_MINB_SMALLK : 1)
 
 struct DtwArgs {
     const int16_t *base;      // base[i] = absolute sample i
@@ -60,9 +65,9 @@ template <> struct DtwNum<float> {
 
 // One wavefront step of one lane: column (t - l) for this lane's K rows.  (ci, si) hold the previous
 // column of these rows, (co, so) receive the new one.
-template <typename T, int K, int L>
+template <typename T, int K, int L, bool RAGGED>
 __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T (&co)[K], int (&so)[K],
-                                         const T (&x)[K], const T *ring, int l, bool pass0, int t, int n,
+                                         const T (&x)[K], const T *ring, int l, bool pass0, int t, int n_last,
                                          T &bot_c, int &bot_s, T &prev_up_c, int &prev_up_s,
                                          T &best, int &best_j, int &best_s)
 {
@@ -83,19 +88,24 @@ __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T
         const bool q = u_c < m1_c;                  // up only if strictly smaller than both
         const T m_c = q ? u_c : m1_c; int m_s = q ? u_s : m1_s;
         T nc = Num::step(x[k], y, m_c);
-        if (k == 0 && pass0) { nc = up_c; m_s = up_s; }
+        if (RAGGED && k == 0 && pass0) { nc = up_c; m_s = up_s; }   // only when L*K != N
         dg_c = lf_c; dg_s = lf_s;
         u_c = nc; u_s = m_s;
         co[k] = nc; so[k] = m_s;
     }
     bot_c = u_c; bot_s = u_s;
-    // running first-argmin of the last row (meaningful in lane L-1 only)
+    // running first-argmin of the last row: n_last is the read length in lane L-1 and 0 elsewhere, so only
+    // the lane that owns the last motif row can fire.  New minima are rare (O(log M) per read), so the update
+    // sits behind a warp vote instead of costing four selects every step.
     const int j = t - (L - 1);
-    if ((unsigned)j < (unsigned)n && bot_c < best) { best = bot_c; best_j = j; best_s = bot_s; }
+    const bool better = (unsigned)j < (unsigned)n_last && bot_c < best;
+    if (__any_sync(SQK_FULL_MASK, better)) {
+        if (better) { best = bot_c; best_j = j; best_s = bot_s; }
+    }
 }
 
-template <typename T, int K, int L>
-__global__ void __launch_bounds__(SQK_DTW_THREADS) sqk_dtw_kernel(const DtwArgs a)
+template <typename T, int K, int L, bool RAGGED>
+__global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kernel(const DtwArgs a)
 {
     constexpr int G = 32 / L;          // reads per warp
     constexpr int RC = 16 * L;         // ring capacity (entries), power of two
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) sqk_dtw_kernel(const DtwArgs 
     int s[K], s2[K];
     T bot_c = Num::inf(), prev_up_c = Num::inf(), best = Num::inf();
     int bot_s = 0, prev_up_s = 0, best_j = -1, best_s = -1;
-    int n = 0, t = 0, wcount = 0, my_read = -1;
+    int n = 0, n_last = 0, t = 0, wcount = 0, my_read = -1;
     int64_t begin = 0, end = 0, cursor = 0;
     double center = 0.0, scale = 1.0;
     bool done = true, exhausted = false;
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) sqk_dtw_kernel(const DtwArgs 
                         }
                     } else {
                         done = false;
+                        n_last = (l == L - 1) ? n : 0;
                         t = 0; wcount = 0;
                         cursor = aligned_block_start(a.base, begin);
 #pragma unroll
@@ -223,9 +234,9 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) sqk_dtw_kernel(const DtwArgs 
         //      so no register-to-register copies are needed to keep the previous column alive) ----
 #pragma unroll 1
         for (int it = 0; it < S; it += 2) {
-            dtw_step<T, K, L>(c, s, c2, s2, x, ring, l, pass0, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+            dtw_step<T, K, L, RAGGED>(c, s, c2, s2, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
             t++;
-            dtw_step<T, K, L>(c2, s2, c, s, x, ring, l, pass0, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+            dtw_step<T, K, L, RAGGED>(c2, s2, c, s, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
             t++;
         }
         __syncwarp();

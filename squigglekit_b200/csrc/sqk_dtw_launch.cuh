@@ -6,13 +6,13 @@
 
 typedef cudaError_t (*sqk_dtw_launcher)(int K, const DtwArgs &a, int n_sms, cudaStream_t st);
 
-template <typename T, int K, int L>
+template <typename T, int K, int L, bool RAGGED>
 static cudaError_t sqk_dtw_launch_one(const DtwArgs &a, int n_sms, cudaStream_t st)
 {
     static int occ = 0;   // resident CTAs per SM for this instantiation
     if (occ == 0) {
         int o = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sqk_dtw_kernel<T, K, L>, SQK_DTW_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sqk_dtw_kernel<T, K, L, RAGGED>, SQK_DTW_THREADS, 0);
         if (e != cudaSuccess) return e;
         occ = o > 0 ? o : 1;
     }
@@ -21,7 +21,7 @@ static cudaError_t sqk_dtw_launch_one(const DtwArgs &a, int n_sms, cudaStream_t 
     long long grid = (long long)n_sms * occ;           // persistent: every CTA resident, groups pull reads
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    sqk_dtw_kernel<T, K, L><<<(unsigned)grid, SQK_DTW_THREADS, 0, st>>>(a);
+    sqk_dtw_kernel<T, K, L, RAGGED><<<(unsigned)grid, SQK_DTW_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -29,7 +29,8 @@ template <typename T, int L, int K, int KMAX>
 struct SqkDtwDispatch {
     static cudaError_t go(int k, const DtwArgs &a, int n_sms, cudaStream_t st)
     {
-        if (k == K) return sqk_dtw_launch_one<T, K, L>(a, n_sms, st);
+        if (k == K)   // motif rows fill the lanes exactly (no pass-through slots) or not
+            return a.N == K * L ? sqk_dtw_launch_one<T, K, L, false>(a, n_sms, st) : sqk_dtw_launch_one<T, K, L, true>(a, n_sms, st);
         if constexpr (K < KMAX) return SqkDtwDispatch<T, L, K + 1, KMAX>::go(k, a, n_sms, st);
         else return cudaErrorInvalidValue;
     }

@@ -30,10 +30,10 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) ub_dtw(int steps, const doubl
     for (int k = 0; k < K; k++) { x[k] = (T)model[(l * K + k) % 80]; c[k] = DtwNum<T>::inf(); s[k] = 0; }
     T bot_c = DtwNum<T>::inf(), prev_up_c = (l == 0) ? (T)0 : DtwNum<T>::inf(), best = DtwNum<T>::inf();
     int bot_s = 0, prev_up_s = 0, best_j = -1, best_s = -1;
-    const int n = steps;
+    const int n = (l == L - 1) ? steps : 0;
     for (int t = 0; t < steps; t += 2) {
-        dtw_step<T, K, L>(c, s, c2, s2, x, ring, l, false, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
-        dtw_step<T, K, L>(c2, s2, c, s, x, ring, l, false, t + 1, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+        dtw_step<T, K, L, false>(c, s, c2, s2, x, ring, l, false, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+        dtw_step<T, K, L, false>(c2, s2, c, s, x, ring, l, false, t + 1, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
     }
     T acc = best + (T)best_j + (T)best_s;
 #pragma unroll
