@@ -144,6 +144,15 @@ typedef struct {
 SQK_API int sqk_segmenter(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
                   int64_t max_read_len, const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
 
+/* Same, on picoamperes: the reference's default for fast5 input converts each read before segmenting,
+ *     pA = np.round((raw + offset) * (range / digitisation), 2)        segmenter.py:345-349, 366-370, 515-517
+ * (range itself pre-rounded to 2 decimals, :344).  pa_offset[n_reads] = channel offset, pa_scale[n_reads] =
+ * range / digitisation, both float64, following `mem`; pa_scale must be > 0.  lim_lo / lim_hi and the
+ * thresholds then apply to the pA values; segment positions are identical to the reference's. */
+SQK_API int sqk_segmenter_pa(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                             int64_t max_read_len, const double *pa_offset, const double *pa_scale,
+                             const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
+
 /* ---------------------------------------------------------------------------------------
  * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the
  * launching stream around each launch.  Off by default.  Reading the counters synchronises.

@@ -11,6 +11,7 @@ container; the DTW is a restatement of un-vendored mlpy 3.5.0 -> "parity unpinne
 from .cpu import (  # noqa: F401
     SegCfg,
     build,
+    convert_to_pa,
     dtw_subsequence,
     dtw_subsequence_rolling,
     get_segs,
@@ -21,5 +22,6 @@ from .cpu import (  # noqa: F401
     np_median,
     np_sum,
     segmenter_batch,
+    segmenter_batch_pa,
     zscale,
 )

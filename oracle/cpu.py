@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
                                          C.c_int, C.c_int, C.c_void_p, ip]
         L.orc_segmenter_batch.argtypes = [C.c_void_p, lp, C.c_int64, C.POINTER(_SegCfg), C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, ip, ip]
+        L.orc_convert_to_pa.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, dp]
+        L.orc_convert_to_pa.restype = None
+        L.orc_segmenter_batch_pa.argtypes = [C.c_void_p, lp, C.c_int64, dp, dp, C.POINTER(_SegCfg), C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, ip, ip]
         _lib = L
     return _lib
 
@@ -195,4 +199,30 @@ def segmenter_batch(signals, offsets, cfg: SegCfg = SegCfg(), lim_lo=0, lim_hi=9
                                    max_segs, n_threads, _ip(segs), _ip(nsegs))
     if rc:
         raise RuntimeError("orc_segmenter_batch failed")
+    return segs, nsegs
+
+
+def convert_to_pa(sig, offset: float, raw_unit: float):
+    """np.round(convert_to_pA_numpy(sig, digitisation, range, offset), 2) with raw_unit = range / digitisation."""
+    sig = np.ascontiguousarray(sig, dtype=np.int16)
+    out = np.empty(sig.size, dtype=np.float64)
+    lib().orc_convert_to_pa(sig.ctypes.data, sig.size, float(offset), float(raw_unit), _dp(out))
+    return out
+
+
+def segmenter_batch_pa(signals, offsets, pa_offset, pa_scale, cfg: SegCfg = SegCfg(), lim_lo=0, lim_hi=900, num=0,
+                       max_segs=16, n_threads=0):
+    """fast5 default path: per read pA conversion -> sig[:Num] -> scale_outliers -> get_segs."""
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    pa_offset = np.ascontiguousarray(pa_offset, dtype=np.float64)
+    pa_scale = np.ascontiguousarray(pa_scale, dtype=np.float64)
+    n = offsets.size - 1
+    segs = np.zeros((n, max_segs, 2), dtype=np.int32)
+    nsegs = np.zeros(n, dtype=np.int32)
+    c = cfg.c()
+    rc = lib().orc_segmenter_batch_pa(signals.ctypes.data, _lp(offsets), n, _dp(pa_offset), _dp(pa_scale), C.byref(c),
+                                      lim_lo, lim_hi, num, max_segs, n_threads, _ip(segs), _ip(nsegs))
+    if rc:
+        raise RuntimeError("orc_segmenter_batch_pa failed")
     return segs, nsegs

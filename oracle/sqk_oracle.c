@@ -441,6 +441,56 @@ ORC_API int orc_segmenter_batch(const int16_t *signals, const int64_t *offsets, 
     return failed ? -1 : 0;
 }
 
+/* convert_to_pA_numpy + np.round(.., 2) (segmenter.py:515-517, 345-349): (d + offset) * raw_unit, then
+ * numpy's round = rint(x * 100) / 100. */
+static inline double pa_value(int d, double offset, double raw_unit)
+{
+    const double x = ((double)d + offset) * raw_unit;
+    return rint(x * 100.0) / 100.0;
+}
+
+ORC_API void orc_convert_to_pa(const int16_t *s, int64_t n, double offset, double raw_unit, double *out)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = pa_value(s[i], offset, raw_unit);
+}
+
+/* fast5 default path of segmenter.py: pA conversion -> sig[:Num] -> scale_outliers on pA -> get_segs. */
+ORC_API int orc_segmenter_batch_pa(const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                                   const double *pa_offset, const double *pa_scale,
+                                   const orc_seg_cfg *cfg, int lim_lo, int lim_hi, int num,
+                                   int max_segs, int n_threads, int32_t *segs, int32_t *n_segs)
+{
+    int failed = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t r = 0; r < n_reads; r++) {
+        int64_t len = offsets[r + 1] - offsets[r];
+        int64_t use;
+        if (num == 0) use = len - 1;
+        else if (num > 0) use = num < len ? num : len;
+        else use = len + num;
+        if (use < 0) use = 0;
+        int cnt = 0;
+        if (use > 0) {
+            double *y = (double *)malloc((size_t)use * sizeof(double));
+            if (!y) failed = 1;
+            else {
+                int64_t kept = 0;
+                for (int64_t i = 0; i < use; i++) {
+                    const double v = pa_value(signals[offsets[r] + i], pa_offset[r], pa_scale[r]);
+                    if (v > lim_lo && v < lim_hi) y[kept++] = v;
+                }
+                if (kept > 0) cnt = orc_get_segs(y, kept, cfg, segs + (size_t)r * max_segs * 2, max_segs, NULL);
+                free(y);
+            }
+        }
+        n_segs[r] = cnt;
+    }
+    return failed ? -1 : 0;
+}
+
 ORC_API int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -4,12 +4,13 @@
 removal (:311-318) and get_segs (:399-470) run in libsqk on the GPU, batched; test_segs (:473-494) is the
 same two comparisons on the host.
 
+fast5 input follows the reference: by default each read is converted to pA rounded to two decimals before
+segmentation (:344-349, :366-370) -- done on the GPU from the raw samples and the per-read calibration --
+and ``--raw_signal`` segments the raw integers.
+
 Deliberate differences, all loud:
-  * fast5 input is segmented on the RAW integer signal (the reference's ``--raw_signal`` behaviour).  The
-    reference's default converts to pA rounded to 2 decimals first (:345-349), which moves the thresholds
-    by a fraction of a sample; float-signal kernels are listed as "next" in DESIGN.md.  Without
-    ``--raw_signal`` a note is written to stderr once.
-  * ``-s`` files with float columns are rejected per read (same reason).
+  * ``-s`` files with float (pA) columns are rejected per read: arbitrary float signal has no int16 form
+    (listed as "next" in DESIGN.md); raw integer columns work.
   * ``-v`` plotting is out of scope -> warning.
 """
 from __future__ import annotations
@@ -71,15 +72,20 @@ def _opener(path):
 
 
 def _fast5_reads(args, path, label):
-    """Yield (name_to_print, int16 signal) the way the reference's branches do: multi-read files print the
-    read group name (segmenter.py:143), single-read files print the file name (:174 / :288)."""
+    """Yield (name_to_print, int16 signal, pa_offset, pa_scale) the way the reference's branches do: multi-read
+    files print the read group name (segmenter.py:143), single-read files print the file name (:174 / :288).
+    pa_scale = float("{0:.2f}".format(range)) / digitisation (:344, :389, :515-517)."""
     from . import fast5 as f5
+
+    def cal(rec):
+        return float(rec["offset"]), float("{0:.2f}".format(rec["range"])) / float(rec["digitisation"])
     try:
         if not args.single:
             for rname, rec in f5.read_multi_fast5(path).items():
-                yield rname, rec["signal"]
+                yield (rname, rec["signal"]) + cal(rec)
         else:
-            yield label, f5.read_single_fast5(path)["signal"]
+            rec = f5.read_single_fast5(path)
+            yield (label, rec["signal"]) + cal(rec)
     except Exception as e:
         sys.stderr.write('process_fast5():failed to extract events or fastq from: {} ({}: {})'.format(path, type(e).__name__, e))
         sys.stderr.write("main():data not extracted. Moving to next file: {}".format(label))
@@ -113,7 +119,7 @@ def iter_reads(args):
                 if sig.min() < -32768 or sig.max() > 32767:
                     sys.stderr.write("{}: samples outside the int16 range\n".format(fast5))
                     continue
-                yield fast5, sig.astype(np.int16)
+                yield fast5, sig.astype(np.int16), 0.0, 1.0
 
 
 def flush(ctx, args, cfg, batch, out):
@@ -123,8 +129,12 @@ def flush(ctx, args, cfg, batch, out):
     sigs = [b[1] for b in batch]
     offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
     np.cumsum([s.size for s in sigs], out=offsets[1:])
-    segs, nsegs = ctx.segmenter(np.concatenate(sigs), offsets, cfg)
-    for (name, _), found in zip(batch, segs_to_lists(segs, nsegs)):
+    if args.signal or args.raw_signal:
+        segs, nsegs = ctx.segmenter(np.concatenate(sigs), offsets, cfg)
+    else:
+        segs, nsegs = ctx.segmenter(np.concatenate(sigs), offsets, cfg, pa_offset=[b[2] for b in batch],
+                                    pa_scale=[b[3] for b in batch])
+    for (name, _, _, _), found in zip(batch, segs_to_lists(segs, nsegs)):
         if not found:
             sys.stderr.write("no segments found: {}".format(name))
             continue
@@ -157,9 +167,6 @@ def main(argv=None):
         sys.exit(1)
     if args.view:
         sys.stderr.write("warning: -v/--view plotting is not part of the GPU port; printing segments only\n")
-    if (args.f5_path or args.ind) and not args.raw_signal:
-        sys.stderr.write("note: segmenting the raw integer signal (as with --raw_signal); pA conversion before "
-                         "segmentation is not implemented in the GPU path\n")
 
     from . import Context, SegConfig
     cfg = SegConfig(error=args.error, corrector=args.corrector, window=args.window, seg_dist=args.seg_dist,

@@ -189,14 +189,22 @@ class Context:
         return hit[0], norm[:n], last[:n]
 
     # ---- segmenter -----------------------------------------------------------------------
-    def segmenter(self, signals, offsets, cfg: SegConfig = SegConfig(), max_read_len: int = 0):
+    def segmenter(self, signals, offsets, cfg: SegConfig = SegConfig(), max_read_len: int = 0, pa_offset=None,
+                  pa_scale=None):
         """Batched ``sig[:Num] -> scale_outliers -> get_segs`` (segmenter.py:124-128,399-470).
+
+        With ``pa_offset`` / ``pa_scale`` (float64 per read: channel offset and range/digitisation) every read
+        is first converted like the reference's fast5 default, ``np.round((raw+offset)*scale, 2)``
+        (segmenter.py:345-349), and limits/thresholds apply to the pA values.
 
         -> (segs int32 [n_reads, max_segs, 2], n_segs int32 [n_reads]); n_segs == 0 is the
         reference's ``False``; n_segs > max_segs means the row was truncated (raise max_segs).
         """
         p = _cabi.SegParams(cfg.error, cfg.corrector, cfg.window, cfg.seg_dist, cfg.std_scale, cfg.stall_len,
                             cfg.lim_low, cfg.lim_hi, cfg.Num, cfg.max_segs)
+        if (pa_offset is None) != (pa_scale is None):
+            raise ValueError("pa_offset and pa_scale go together")
+        use_pa = pa_offset is not None
         if _is_torch(signals):
             import torch
             if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
@@ -206,17 +214,34 @@ class Context:
             segs = torch.zeros((n_reads, cfg.max_segs, 2), dtype=torch.int32, device=dev)
             nsegs = torch.zeros(n_reads, dtype=torch.int32, device=dev)
             self._use_torch_stream()
-            _cabi.check(self._lib.sqk_segmenter(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads,
-                                                int(max_read_len), C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(),
-                                                nsegs.data_ptr()))
+            if use_pa:
+                po = torch.as_tensor(pa_offset, dtype=torch.float64, device=dev).contiguous()
+                ps = torch.as_tensor(pa_scale, dtype=torch.float64, device=dev).contiguous()
+                _cabi.check(self._lib.sqk_segmenter_pa(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads,
+                                                       int(max_read_len), po.data_ptr(), ps.data_ptr(), C.byref(p),
+                                                       _cabi.SQK_MEM_DEVICE, segs.data_ptr(), nsegs.data_ptr()))
+                self._keepalive = (po, ps)     # stream-ordered use: keep the tensors alive until the next call
+            else:
+                _cabi.check(self._lib.sqk_segmenter(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads,
+                                                    int(max_read_len), C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(),
+                                                    nsegs.data_ptr()))
             return segs, nsegs
         signals = np.ascontiguousarray(signals, dtype=np.int16)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n_reads = offsets.size - 1
         segs = np.zeros((n_reads, cfg.max_segs, 2), dtype=np.int32)
         nsegs = np.zeros(n_reads, dtype=np.int32)
-        _cabi.check(self._lib.sqk_segmenter(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
-                                            C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
+        if use_pa:
+            po = np.ascontiguousarray(pa_offset, dtype=np.float64)
+            ps = np.ascontiguousarray(pa_scale, dtype=np.float64)
+            if po.size != n_reads or ps.size != n_reads:
+                raise ValueError("pa_offset / pa_scale need one value per read")
+            _cabi.check(self._lib.sqk_segmenter_pa(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads,
+                                                   int(max_read_len), po.ctypes.data, ps.ctypes.data, C.byref(p),
+                                                   _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
+        else:
+            _cabi.check(self._lib.sqk_segmenter(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
+                                                C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
         return segs, nsegs
 
 

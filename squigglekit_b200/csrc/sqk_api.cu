@@ -93,7 +93,7 @@ struct Pending { void *dst; const void *src; size_t bytes; };
 
 struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
-    DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage;
+    DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale;
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -296,9 +296,13 @@ struct View {                 // a set of reads resident on the device
     int64_t max_len;
 };
 
+static inline int clamp_lim(int v) { return v < -40000 ? -40000 : (v > 40000 ? 40000 : v); }   // samples are int16
+
 static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
-                        double std_scale, int32_t *d_nkept)
+                        double std_scale, int32_t *d_nkept, const double *d_pa_off = nullptr,
+                        const double *d_pa_scale = nullptr)
 {
+    lo = clamp_lim(lo); hi = clamp_lim(hi);
     TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
     const int static_smem = (int)sizeof(StatsShared) + 64;
     const int cap_max = (c->smem_optin - static_smem - 1024) / 2;
@@ -319,6 +323,7 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = v.n_reads;
     a.stats = (ReadStats *)s.stats.p; a.n_kept_out = d_nkept;
     a.mode = mode; a.lo = lo; a.hi = hi; a.num = num; a.std_scale = std_scale;
+    a.pa_offset = d_pa_off; a.pa_scale = d_pa_scale;
     a.cap = (int)cap; a.gstage = nullptr; a.gstage_stride = 0;
     if (v.max_len > cap && mode != SQK_STATS_NONE) {
         const int64_t stride = (v.max_len + 7) & ~7ll;
@@ -399,7 +404,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
         a.stats = (const ReadStats *)s.stats.p;
         a.model = d_models + h_model_offsets[m]; a.N = N;
-        a.lo = p->lo; a.hi = p->hi;
+        a.lo = clamp_lim(p->lo); a.hi = clamp_lim(p->hi);
         a.hits = d_hits + m; a.hit_stride = n_models;
         a.counter = (unsigned *)s.counter.p + m;
         cudaEvent_t eb;
@@ -421,16 +426,16 @@ static int check_seg_params(const sqk_seg_params *p)
 }
 
 static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const sqk_seg_params *p,
-                             int32_t *d_segs, int32_t *d_nsegs)
+                             int32_t *d_segs, int32_t *d_nsegs, const double *d_pa_off, const double *d_pa_scale)
 {
     if (v.n_reads == 0) return SQK_OK;
     if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
-    TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr));
+    TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr, d_pa_off, d_pa_scale));
     FsmArgs a{};
     a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
     a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
     a.stats = (const ReadStats *)s.stats.p;
-    a.lo = p->lim_lo; a.hi = p->lim_hi; a.num = p->num;
+    a.num = p->num;
     a.error = p->error; a.corrector = p->corrector; a.window = p->window; a.seg_dist = p->seg_dist;
     const double fm = std::ceil((double)p->window * p->stall_len);
     a.first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
@@ -542,7 +547,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
     for (int i = 0; i < 2; i++) {
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
-        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -686,9 +691,13 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     return SQK_OK;
 }
 
-int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
-                  const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)
+}  // extern "C"
+
+static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                          const double *pa_offset, const double *pa_scale, const sqk_seg_params *p, int mem, int32_t *segs,
+                          int32_t *n_segs)
 {
+    if ((pa_offset == nullptr) != (pa_scale == nullptr)) return fail(SQK_ERR_ARG, "pa_offset and pa_scale must be given together");
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
     if (n_reads < 0) return fail(SQK_ERR_ARG, "n_reads < 0");
     if (n_reads == 0) return SQK_OK;
@@ -704,7 +713,7 @@ int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, in
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
         if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
-        TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs));
+        TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale));
         return SQK_OK;
     }
 
@@ -732,14 +741,38 @@ int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, in
         if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(s.segs.p, 0, (size_t)nr * seg_row, st));
+        const double *d_po = nullptr, *d_ps = nullptr;
+        if (pa_offset) {
+            TRY(ensure(s.pa_off, (size_t)nr * sizeof(double)));
+            TRY(ensure(s.pa_scale, (size_t)nr * sizeof(double)));
+            CU(cudaMemcpyAsync(s.pa_off.p, pa_offset + r0, (size_t)nr * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s.pa_scale.p, pa_scale + r0, (size_t)nr * sizeof(double), cudaMemcpyHostToDevice, st));
+            d_po = (const double *)s.pa_off.p - r0; d_ps = (const double *)s.pa_scale.p - r0;
+        }
         View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
-        TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
+        TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p, d_po, d_ps));
         TRY(result_to_host(s, 0, (char *)segs + (size_t)r0 * seg_row, s.segs.p, (size_t)nr * seg_row, segs_pinned));
         TRY(result_to_host(s, 1, n_segs + r0, s.nsegs.p, (size_t)nr * sizeof(int32_t), nsegs_pinned));
     }
     TRY(recycle(c->slot[0]));
     TRY(recycle(c->slot[1]));
     return SQK_OK;
+}
+
+extern "C" {
+
+int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                  const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)
+{
+    return segmenter_impl(c, signals, offsets, n_reads, max_read_len, nullptr, nullptr, p, mem, segs, n_segs);
+}
+
+int sqk_segmenter_pa(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                     const double *pa_offset, const double *pa_scale, const sqk_seg_params *p, int mem, int32_t *segs,
+                     int32_t *n_segs)
+{
+    if (!pa_offset || !pa_scale) return fail(SQK_ERR_ARG, "pa_offset/pa_scale is NULL");
+    return segmenter_impl(c, signals, offsets, n_reads, max_read_len, pa_offset, pa_scale, p, mem, segs, n_segs);
 }
 
 int sqk_motifseq_trace(sqk_ctx *c, const int16_t *signal, int64_t n_samples, const double *model, int32_t n_model,

@@ -18,10 +18,21 @@ struct __align__(8) ReadStats {
     int32_t flags;    // bit0: degenerate scale (MAD == 0)
     int32_t seg_lo;
     int32_t seg_hi;
+    int32_t out_lo;   // outlier window on the raw sample, inclusive: kept  <=>  out_lo <= s <= out_hi
+    int32_t out_hi;   //   (raw mode: lo+1 .. hi-1; pA mode: the raw values whose pA lies in (lim_low, lim_hi))
 };
-static_assert(sizeof(ReadStats) == 32, "ReadStats layout");
+static_assert(sizeof(ReadStats) == 40, "ReadStats layout");
 
 #define SQK_FLAG_DEGENERATE 1
+
+// convert_to_pA_numpy + np.round(.., 2)  (segmenter.py:515-517, 345-349): every op rounds once, as numpy's
+//   (d + offset) * raw_unit ; multiply by 100 ; rint ; divide by 100.
+// Monotone non-decreasing in d for raw_unit > 0, so windows on pA are windows on d.
+__device__ __forceinline__ double sqk_pa_value(int d, double offset, double raw_unit)
+{
+    const double x = __dmul_rn(__dadd_rn((double)d, offset), raw_unit);
+    return __ddiv_rn(rint(__dmul_rn(x, 100.0)), 100.0);
+}
 
 // python  sig[:Num]  with Num = num ? num : -1   (segmenter.py:104-105,207)
 __host__ __device__ __forceinline__ int64_t sqk_truncate_len(int64_t len, int num)

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs 
     const int64_t begin = a.offsets[r];
     const int64_t end = begin + sqk_truncate_len(a.offsets[r + 1] - begin, a.num);
     const ReadStats st = a.stats[i];
-    const int seg_lo = st.seg_lo, seg_hi = st.seg_hi;
+    const int seg_lo = st.seg_lo, seg_hi = st.seg_hi, out_lo = st.out_lo, out_hi = st.out_hi;
     int32_t *out = a.segs + (int64_t)i * a.max_segs * 2;
 
     bool open = false;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs 
         for (int e = 0; e < 8; e++) {
             const int64_t idx = blk + e;
             const int v = smp.get(e);
-            if (idx < begin || idx >= end || !(v > a.lo && v < a.hi)) continue;   // scale_outliers
+            if (idx < begin || idx >= end || v < out_lo || v > out_hi) continue;   // scale_outliers
             if (v >= seg_lo && v <= seg_hi) {
                 if (!open) { start = pos; open = true; }
                 c++; w++;

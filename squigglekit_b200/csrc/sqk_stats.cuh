@@ -36,6 +36,8 @@ struct StatsArgs {
     int32_t *n_kept_out;      // [n_reads] or null
     int mode, lo, hi, num;
     double std_scale;
+    const double *pa_offset;  // segmenter pA mode: per-read calibration, indexable by absolute read id (or null)
+    const double *pa_scale;   //   pA = round((d + pa_offset) * pa_scale, 2)
     int cap;                  // shared-memory staging capacity (samples)
     int16_t *gstage;          // global staging rows for reads longer than cap (or null)
     int64_t gstage_stride;
@@ -55,36 +57,28 @@ struct StatsShared {
     double result;
 };
 
-// numpy pairwise leaf (n <= 128) over sq[i] = fl(fl(x_i - mean)^2), evaluated by an 8-lane team.
-__device__ __forceinline__ double stats_leaf_sum(const int16_t *x, int off, int len, double mean, int k)
+// numpy pairwise leaf (n <= 128) over term(i), evaluated by an 8-lane team (lane k = accumulator k).
+template <class Term>
+__device__ __forceinline__ double stats_leaf_sum(Term term, int off, int len, int k)
 {
     if (len < 8) {
         double r = 0.0;
-        for (int i = 0; i < len; i++) {
-            const double d = __dsub_rn((double)x[off + i], mean);
-            r = __dadd_rn(r, __dmul_rn(d, d));
-        }
+        for (int i = 0; i < len; i++) r = __dadd_rn(r, term(off + i));
         return r;
     }
     const int body = len - (len & 7);
-    double d = __dsub_rn((double)x[off + k], mean);
-    double r = __dmul_rn(d, d);
-    for (int i = 8; i < body; i += 8) {
-        d = __dsub_rn((double)x[off + i + k], mean);
-        r = __dadd_rn(r, __dmul_rn(d, d));
-    }
+    double r = term(off + k);
+    for (int i = 8; i < body; i += 8) r = __dadd_rn(r, term(off + i + k));
     r = __dadd_rn(r, shfl_xor_f64(r, 1, 8));   // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
     r = __dadd_rn(r, shfl_xor_f64(r, 2, 8));   // ((r0+r1)+(r2+r3)) ...
     r = __dadd_rn(r, shfl_xor_f64(r, 4, 8));
-    for (int i = body; i < len; i++) {
-        d = __dsub_rn((double)x[off + i], mean);
-        r = __dadd_rn(r, __dmul_rn(d, d));
-    }
+    for (int i = body; i < len; i++) r = __dadd_rn(r, term(off + i));
     return r;
 }
 
-// S = np.sum((x - mean)**2) for the n staged samples; result valid in every thread.
-__device__ double stats_pairwise_sq(const int16_t *x, int n, double mean, StatsShared &sh)
+// np.sum over term(0..n-1) in numpy's pairwise order; result valid in every thread.
+template <class Term>
+__device__ double stats_pairwise(Term term, int n, StatsShared &sh)
 {
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -117,7 +111,7 @@ __device__ double stats_pairwise_sq(const int16_t *x, int n, double mean, StatsS
         for (int q = team; q < ((nl + SQK_STATS_TEAMS - 1) / SQK_STATS_TEAMS) * SQK_STATS_TEAMS; q += SQK_STATS_TEAMS) {
             // whole warps stay converged for the shuffles; surplus teams redo the last leaf
             const int qq = q < nl ? q : nl - 1;
-            const double s = stats_leaf_sum(x, sh.lf_off[qq], sh.lf_len[qq], mean, k);
+            const double s = stats_leaf_sum(term, sh.lf_off[qq], sh.lf_len[qq], k);
             if (q < nl && k == 0) sh.lf_sum[q] = s;
         }
         __syncthreads();
@@ -183,6 +177,28 @@ __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
     return prefix;
 }
 
+// smallest d in [-32768, 32767] with pa(d) > limit  (32768 if none);  pa is monotone in d
+__device__ __forceinline__ int stats_first_above(double limit, double off, double unit)
+{
+    int lo = -32768, hi = 32768;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (sqk_pa_value(mid, off, unit) > limit) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// largest d in [-32768, 32767] with pa(d) < limit  (-32769 if none)
+__device__ __forceinline__ int stats_last_below(double limit, double off, double unit)
+{
+    int lo = -32769, hi = 32767;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo + 1) >> 1);
+        if (sqk_pa_value(mid, off, unit) < limit) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const StatsArgs a)
 {
     extern __shared__ __align__(16) int16_t smem_stage[];
@@ -190,6 +206,7 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
     resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
+    const bool pa_mode = (a.mode == SQK_STATS_SEGMENTER && a.pa_offset != nullptr);
 
     for (int64_t i = blockIdx.x; i < a.n_reads; i += gridDim.x) {
         const int64_t r = a.read0 + i;
@@ -199,6 +216,20 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
         const int64_t end = begin + len;
         const bool staged = (a.mode != SQK_STATS_NONE);
         int16_t *stage = (len <= a.cap) ? smem_stage : a.gstage + (int64_t)blockIdx.x * a.gstage_stride;
+
+        // ---- outlier window on the raw sample (inclusive) ------------------------------------
+        int out_lo = a.lo + 1, out_hi = a.hi - 1;
+        double pa_off = 0.0, pa_unit = 1.0;
+        if (pa_mode) {
+            // lim_low < pA(d) < lim_hi  <=>  out_lo <= d <= out_hi   (pA is monotone in d)
+            pa_off = a.pa_offset[r]; pa_unit = a.pa_scale[r];
+            if (pa_unit > 0.0) {
+                out_lo = stats_first_above((double)a.lo, pa_off, pa_unit);
+                out_hi = stats_last_below((double)a.hi, pa_off, pa_unit);
+            } else {
+                out_lo = 1; out_hi = 0;   // unusable calibration: keep nothing, report no segments
+            }
+        }
 
         // ---- pass over HBM: filter, compact, integer sum ------------------------------------
         long long sum = 0;
@@ -214,7 +245,7 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 for (int e = 0; e < 8; e++) {
                     const int v = s.get(e);
                     const int64_t idx = blk + e;
-                    if (idx >= begin && idx < end && v > a.lo && v < a.hi) { keep |= 1u << e; sum += v; }
+                    if (idx >= begin && idx < end && v >= out_lo && v <= out_hi) { keep |= 1u << e; sum += v; }
                 }
             }
             const int cnt = __popc(keep);
@@ -254,30 +285,42 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
 
         ReadStats out;
         out.center = 0.0; out.scale = 1.0; out.n_kept = n; out.flags = 0; out.seg_lo = 0; out.seg_hi = -1;
+        out.out_lo = out_lo; out.out_hi = out_hi;
 
+        double sd = 0.0;
         if (n > 0 && (a.mode == SQK_STATS_ZSCALE || a.mode == SQK_STATS_SEGMENTER)) {
-            const double mean = __ddiv_rn((double)tot_sum, (double)n);
-            const double S = stats_pairwise_sq(stage, n, mean, sh);
-            double sd = __dsqrt_rn(__ddiv_rn(S, (double)n));
+            if (!pa_mode) {
+                // integer samples: the sum is exact in any order
+                const double mean = __ddiv_rn((double)tot_sum, (double)n);
+                auto sq = [stage, mean](int q) -> double { const double d = __dsub_rn((double)stage[q], mean); return __dmul_rn(d, d); };
+                sd = __dsqrt_rn(__ddiv_rn(stats_pairwise(sq, n, sh), (double)n));
+            } else {
+                // pA samples are not integers: np.std's mean is itself a pairwise sum
+                auto val = [stage, pa_off, pa_unit](int q) -> double { return sqk_pa_value((int)stage[q], pa_off, pa_unit); };
+                const double mean = __ddiv_rn(stats_pairwise(val, n, sh), (double)n);
+                auto sq = [stage, pa_off, pa_unit, mean](int q) -> double {
+                    const double d = __dsub_rn(sqk_pa_value((int)stage[q], pa_off, pa_unit), mean);
+                    return __dmul_rn(d, d);
+                };
+                sd = __dsqrt_rn(__ddiv_rn(stats_pairwise(sq, n, sh), (double)n));
+            }
             if (a.mode == SQK_STATS_ZSCALE) {
                 if (sd == 0.0) sd = 1.0;          // sklearn _handle_zeros_in_scale
-                out.center = mean; out.scale = sd;
-            } else {
-                out.scale = sd;                    // finished below once the median is known
+                out.center = __ddiv_rn((double)tot_sum, (double)n); out.scale = sd;
             }
         }
         if (n > 0 && (a.mode == SQK_STATS_MEDMAD || a.mode == SQK_STATS_SEGMENTER)) {
             auto key_x = [stage](int q) -> uint32_t { return (uint32_t)((int)stage[q] + 32768); };
-            int med2;   // 2 * median, integer
+            int lo_v, hi_v;   // the two middle order statistics (equal for odd n)
             if (n & 1) {
-                med2 = 2 * ((int)stats_select(key_x, n, (n - 1) / 2, sh) - 32768);
+                lo_v = hi_v = (int)stats_select(key_x, n, (n - 1) / 2, sh) - 32768;
             } else {
-                const int lo_v = (int)stats_select(key_x, n, n / 2 - 1, sh) - 32768;
-                const int hi_v = (int)stats_select(key_x, n, n / 2, sh) - 32768;
-                med2 = lo_v + hi_v;
+                lo_v = (int)stats_select(key_x, n, n / 2 - 1, sh) - 32768;
+                hi_v = (int)stats_select(key_x, n, n / 2, sh) - 32768;
             }
-            const double median = (double)med2 * 0.5;
+            const int med2 = lo_v + hi_v;   // 2 * median of the raw integers
             if (a.mode == SQK_STATS_MEDMAD) {
+                const double median = (double)med2 * 0.5;
                 auto key_d = [stage, med2](int q) -> uint32_t {
                     const int d = 2 * (int)stage[q] - med2;
                     return (uint32_t)(d < 0 ? -d : d);
@@ -294,14 +337,24 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 out.center = median; out.scale = scaled;
                 if (scaled == 0.0) out.flags |= SQK_FLAG_DEGENERATE;
             } else {
-                const double spread = __dmul_rn(out.scale, a.std_scale);
+                double median;
+                if (!pa_mode) median = (double)med2 * 0.5;
+                else if (n & 1) median = sqk_pa_value(lo_v, pa_off, pa_unit);
+                else median = __ddiv_rn(__dadd_rn(sqk_pa_value(lo_v, pa_off, pa_unit), sqk_pa_value(hi_v, pa_off, pa_unit)), 2.0);
+                const double spread = __dmul_rn(sd, a.std_scale);
                 const double top = __dadd_rn(median, spread);
                 const double bot = __dsub_rn(median, spread);
-                // integer x:  x < top  <=>  x <= ceil(top)-1 ;  x > bot  <=>  x >= floor(bot)+1
-                const double hi_d = fmin(fmax(ceil(top) - 1.0, -40000.0), 40000.0);
-                const double lo_d = fmin(fmax(floor(bot) + 1.0, -40000.0), 40000.0);
-                out.seg_hi = (top == top) ? (int)hi_d : -40000;   // NaN threshold: nothing is in range
-                out.seg_lo = (bot == bot) ? (int)lo_d : 40000;
+                if (!pa_mode) {
+                    // integer x:  x < top  <=>  x <= ceil(top)-1 ;  x > bot  <=>  x >= floor(bot)+1
+                    const double hi_d = fmin(fmax(ceil(top) - 1.0, -40000.0), 40000.0);
+                    const double lo_d = fmin(fmax(floor(bot) + 1.0, -40000.0), 40000.0);
+                    out.seg_hi = (top == top) ? (int)hi_d : -40000;   // NaN threshold: nothing is in range
+                    out.seg_lo = (bot == bot) ? (int)lo_d : 40000;
+                } else {
+                    // pA(d) < top  <=>  d <= last_below(top);  pA(d) > bot  <=>  d >= first_above(bot)
+                    out.seg_hi = (top == top) ? stats_last_below(top, pa_off, pa_unit) : -40000;
+                    out.seg_lo = (bot == bot) ? stats_first_above(bot, pa_off, pa_unit) : 40000;
+                }
                 out.center = top; out.scale = bot;
             }
         }

@@ -166,6 +166,39 @@ def main():
     with open(os.path.join(HERE, "segmenter_golden.json"), "w") as f:
         json.dump(seg_out, f)
 
+    # ---- segmenter, fast5 default path: pA conversion (convert_to_pA_numpy + np.round) before get_segs ----
+    n_reads = soff.size - 1
+    rng = np.random.default_rng(17)
+    cal_offset = rng.integers(-30, 40, n_reads).astype(float)
+    cal_range = np.round(rng.uniform(1100.0, 1600.0, n_reads), 2)
+    digitisation = 8192.0
+    pa_sets = [dict(), dict(stall=True, test=True), dict(lim_hi=120, lim_low=40, window=60),
+               dict(error=80, corrector=0, window=10), dict(Num=1200, std_scale=0.5)]
+    pa_out = []
+    for ps in pa_sets:
+        a = refload.Args(**ps)
+        per_read = []
+        for r in range(n_reads):
+            raw_r = np.array(ssig[soff[r]:soff[r + 1]], dtype=int)
+            rg = float("{0:.2f}".format(cal_range[r]))                       # segmenter.py:344
+            pa = np.round(seg.convert_to_pA_numpy(raw_r, digitisation, rg, cal_offset[r]), 2)
+            sig = np.array(pa[:a.Num], dtype=float)
+            sig = seg.scale_outliers(sig, a)
+            if sig.size == 0:
+                per_read.append(None)
+                continue
+            segs = seg.get_segs(sig, a)
+            tested = None
+            if segs and a.test:
+                with contextlib.redirect_stderr(io.StringIO()):
+                    tested = seg.test_segs([list(s) for s in segs], a)
+            per_read.append({"segs": segs if segs else False,
+                             "tested": (tested if tested else False) if a.test else None})
+        pa_out.append({"params": ps, "reads": per_read})
+    with open(os.path.join(HERE, "segmenter_pa_golden.json"), "w") as f:
+        json.dump({"offset": cal_offset.tolist(), "range": cal_range.tolist(), "digitisation": digitisation,
+                   "cases": pa_out}, f)
+
     # ---- numpy pairwise-sum known answers (pins oracle.np_sum and the CUDA sigma tree) -----
     rng = np.random.default_rng(11)
     sums = {}

@@ -80,3 +80,12 @@ def test_segmenter_single_fast5(golden_dir):
     path = os.path.join(golden_dir, "test.fast5")
     out, _ = run("segmenter.py", "-i", path, "--single", "--raw_signal")
     assert out.rstrip("\n") == path + "\t" + ",".join(f"{a},{b}" for a, b in exp["segs_raw"])
+
+
+def test_segmenter_single_fast5_default_is_pa(golden_dir):
+    """Without --raw_signal the reference segments pA rounded to 2 decimals (segmenter.py:345-349)."""
+    exp = json.load(open(os.path.join(golden_dir, "example_expected.json")))
+    path = os.path.join(golden_dir, "test.fast5")
+    out, _ = run("segmenter.py", "-i", path, "--single")
+    assert out.rstrip("\n") == path + "\t" + ",".join(f"{a},{b}" for a, b in exp["segs_pA"])
+    assert exp["segs_pA"] != exp["segs_raw"]

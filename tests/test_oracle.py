@@ -137,3 +137,27 @@ def test_against_reference_tree_live():
             assert seg.get_segs(s, a) == oracle.get_segs(s, cfg, max_segs=512)
     model, order, L = ms.read_synth_model(os.path.join(refload.REFERENCE_ROOT, "example", "CATCTATCCAGGGTTAAATT.model"))
     assert (order, L, len(model[order[0]])) == (["3_prime_end"], [20], 163)
+
+
+def test_get_segs_pa_goldens(golden_dir):
+    """fast5 default path (pA conversion first): oracle vs the reference's own convert_to_pA_numpy + get_segs."""
+    g = np.load(os.path.join(golden_dir, "segmenter_inputs.npz"))
+    gold = json.load(open(os.path.join(golden_dir, "segmenter_pa_golden.json")))
+    off = np.array(gold["offset"])
+    scale = np.array([float("{0:.2f}".format(v)) for v in gold["range"]]) / gold["digitisation"]
+    for case in gold["cases"]:
+        p = case["params"]
+        cfg = oracle.SegCfg(**{k: p[k] for k in ("error", "corrector", "window", "seg_dist", "std_scale", "stall_len") if k in p})
+        segs, n = oracle.segmenter_batch_pa(g["signals"], g["offsets"], off, scale, cfg, p.get("lim_low", 0),
+                                            p.get("lim_hi", 900), p.get("Num", 0), 512)
+        for r, want in enumerate(case["reads"]):
+            got = segs[r, :n[r]].tolist() if n[r] else False
+            assert got == (want["segs"] if want is not None else False), (p, r)
+
+
+def test_pa_conversion_matches_numpy_round():
+    rng = np.random.default_rng(4)
+    raw = rng.integers(-200, 2000, 5000).astype(np.int16)
+    for offset, rg, dig in ((16.0, 1493.94, 8192.0), (-7.0, 1234.56, 8192.0), (3.0, 1467.61, 2048.0)):
+        want = np.round((raw.astype(int) + offset) * (rg / dig), 2)
+        assert np.array_equal(oracle.convert_to_pa(raw, offset, rg / dig), want)

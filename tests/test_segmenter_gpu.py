@@ -110,3 +110,62 @@ def test_config2_size(ctx):
     # the planted stall is found near the start in most reads
     first = segs[:, 0, 0][want_n > 0]
     assert (first <= cfg.stall_start).mean() > 0.8
+
+
+def _pa_cal(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "segmenter_pa_golden.json")))
+    off = np.array(gold["offset"])
+    scale = np.array([float("{0:.2f}".format(v)) for v in gold["range"]]) / gold["digitisation"]
+    return gold, off, scale
+
+
+def test_pa_mode_golden_reference_outputs(ctx, golden_dir):
+    """a9: convert_to_pA_numpy + np.round(.., 2) before get_segs -- the reference's fast5 default."""
+    g = np.load(os.path.join(golden_dir, "segmenter_inputs.npz"))
+    gold, off, scale = _pa_cal(golden_dir)
+    for case in gold["cases"]:
+        cfg = cfg_from(case["params"])
+        segs, nsegs = ctx.segmenter(g["signals"], g["offsets"], cfg, pa_offset=off, pa_scale=scale)
+        got = sqk.segs_to_lists(segs, nsegs)
+        for r, want in enumerate(case["reads"]):
+            if want is None:
+                assert got[r] is False
+                continue
+            assert got[r] == want["segs"], (case["params"], r)
+            if want["tested"] is not None:
+                assert sqk.test_segs(got[r], cfg) == want["tested"], (case["params"], r)
+
+
+def test_pa_mode_example_read(ctx, golden_dir):
+    ex = np.load(os.path.join(golden_dir, "example_read.npz"), allow_pickle=True)
+    want = json.load(open(os.path.join(golden_dir, "example_expected.json")))["segs_pA"]
+    raw = ex["raw"]
+    segs, nsegs = ctx.segmenter(raw, np.array([0, raw.size], dtype=np.int64), sqk.SegConfig(),
+                                pa_offset=[16.0], pa_scale=[float("{0:.2f}".format(1493.94)) / 8192.0])
+    assert sqk.segs_to_lists(segs, nsegs)[0] == want
+
+
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_pa_mode_synthetic_vs_oracle(ctx, mode):
+    sig, off = synth.segmenter_reads_np(300, 4096, seed=21)
+    extra, eoff = synth.ragged_reads_np([0, 1, 2, 9, 150, 151, 700, 9000])
+    sig = np.concatenate([sig, extra])
+    off = np.concatenate([off, off[-1] + eoff[1:]])
+    n = off.size - 1
+    rng = np.random.default_rng(8)
+    po = rng.integers(-30, 40, n).astype(float)
+    ps = np.round(rng.uniform(1100, 1600, n), 2) / 8192.0
+    for params in (dict(), dict(lim_hi=120, lim_low=40, window=60), dict(error=80, corrector=0, window=10), dict(Num=2000)):
+        cfg = cfg_from(params)
+        ocfg = oracle.SegCfg(cfg.error, cfg.corrector, cfg.window, cfg.seg_dist, cfg.std_scale, cfg.stall_len)
+        want, want_n = oracle.segmenter_batch_pa(sig, off, po, ps, ocfg, cfg.lim_low, cfg.lim_hi, cfg.Num, cfg.max_segs)
+        if mode == "device":
+            import torch
+            s_t, n_t = ctx.segmenter(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), cfg, pa_offset=po, pa_scale=ps)
+            torch.cuda.synchronize()
+            segs, nsegs = s_t.cpu().numpy(), n_t.cpu().numpy()
+        else:
+            segs, nsegs = ctx.segmenter(sig, off, cfg, pa_offset=po, pa_scale=ps)
+        assert np.array_equal(nsegs, want_n), (params, np.nonzero(nsegs != want_n)[0][:10])
+        for r in range(n):
+            assert np.array_equal(segs[r, :nsegs[r]], want[r, :want_n[r]]), (params, r)
