@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -470,9 +471,11 @@ static void plan_chunks(const int64_t *offsets, int64_t n_reads, int64_t target,
     cuts.clear();
     cuts.push_back(0);
     int64_t r = 0;
+    int ramp = 2;   // first chunks are 1/4 and 1/2 of the target: the GPU starts after a short first copy
     while (r < n_reads) {
         int64_t e = r + 1;
-        const int64_t lim = offsets[r] + target;
+        const int64_t lim = offsets[r] + (target >> ramp);
+        if (ramp > 0) ramp--;
         // gallop + binary search for the last read ending within the target
         int64_t lo = e, hi = n_reads;
         while (lo < hi) {
@@ -486,7 +489,16 @@ static void plan_chunks(const int64_t *offsets, int64_t n_reads, int64_t target,
     }
 }
 
-static const int64_t kChunkSamples = 64ll << 20;   // 128 MiB of int16 per in-flight chunk: >= one full wave of CTAs at 4k samples/read
+static int64_t chunk_samples()   // samples per in-flight chunk; default 64 Mi (128 MiB of int16): >= one full wave of CTAs at 4k samples/read
+{
+    static int64_t v = 0;
+    if (v == 0) {
+        const char *e = getenv("SQK_CHUNK_SAMPLES");   // tuning knob for experiments
+        v = e ? atoll(e) : 0;
+        if (v < (1 << 16)) v = 64ll << 20;
+    }
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------
 // exported API
@@ -666,7 +678,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
     CU(cudaStreamSynchronize(c->slot[0].stream));
     std::vector<int64_t> cuts;
-    plan_chunks(offsets, n_reads, kChunkSamples, cuts);
+    plan_chunks(offsets, n_reads, chunk_samples(), cuts);
     const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
@@ -726,7 +738,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     }
     if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
     std::vector<int64_t> cuts;
-    plan_chunks(offsets, n_reads, kChunkSamples, cuts);
+    plan_chunks(offsets, n_reads, chunk_samples(), cuts);
     const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];

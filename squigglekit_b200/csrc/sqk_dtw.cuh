@@ -104,6 +104,40 @@ __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T
     }
 }
 
+// Cost-only variant of dtw_step: same values bit for bit (min3 is order-free), no start pointers --
+// 4 instead of 6 ALU-pipe selects per cell.  Used by the two-pass scheme: this pass finds end and dist,
+// a short pointer-carrying re-run from a saved column state recovers start (sqk_dtw2.cuh).
+template <typename T, int K, int L, bool RAGGED>
+__device__ __forceinline__ void dtw_step_cost(const T (&ci)[K], T (&co)[K], const T (&x)[K], const T *ring, int l,
+                                              bool pass0, int t, int n_last, T &bot_c, T &prev_up_c, T &best, int &best_j)
+{
+    using Num = DtwNum<T>;
+    constexpr int RC = 16 * L;
+    T up_c = Num::shfl_up(bot_c, L);
+    if (l == 0) up_c = (T)0;
+    const T y = ring[(t - l) & (RC - 1)];
+    T dg_c = prev_up_c;
+    prev_up_c = up_c;
+    T u_c = up_c;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const T lf_c = ci[k];
+        const T m1_c = lf_c < dg_c ? lf_c : dg_c;
+        const T m_c = u_c < m1_c ? u_c : m1_c;
+        T nc = Num::step(x[k], y, m_c);
+        if (RAGGED && k == 0 && pass0) nc = up_c;
+        dg_c = lf_c;
+        u_c = nc;
+        co[k] = nc;
+    }
+    bot_c = u_c;
+    const int j = t - (L - 1);
+    const bool better = (unsigned)j < (unsigned)n_last && bot_c < best;
+    if (__any_sync(SQK_FULL_MASK, better)) {
+        if (better) { best = bot_c; best_j = j; }
+    }
+}
+
 template <typename T, int K, int L, bool RAGGED>
 __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kernel(const DtwArgs a)
 {
