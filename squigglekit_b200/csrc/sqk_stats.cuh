@@ -23,7 +23,10 @@
 #define SQK_STATS_TEAMS (SQK_STATS_THREADS / 8)
 #define SQK_LEAF_BATCH 64
 #define SQK_TREE_DEPTH 48
-#define SQK_HIST_BINS 512
+#define SQK_HIST_BINS 2048          // direct histogram when the outlier window spans <= 2048 raw values
+#define SQK_RADIX_BINS 512          // fallback two-pass radix select (9 + 8 bits)
+#define SQK_HEAP_NODES 512          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
+#define SQK_HEAP_MAX_N 8192
 
 enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3 };
 
@@ -55,6 +58,9 @@ struct StatsShared {
     int cs_dep[SQK_TREE_DEPTH];
     int sp, csp, nleaf;
     double result;
+    int hp_off[SQK_HEAP_NODES], hp_len[SQK_HEAP_NODES];
+    double hp_sum[SQK_HEAP_NODES];
+    uint32_t scan_part[SQK_STATS_WARPS];
 };
 
 // numpy pairwise leaf (n <= 128) over term(i), evaluated by an 8-lane team (lane k = accumulator k).
@@ -134,7 +140,129 @@ __device__ double stats_pairwise(Term term, int n, StatsShared &sh)
     return sh.result;
 }
 
-// rank-th smallest (0-based) of key(i), i < n, keys < 512*256.  Two-pass radix select.
+// Same sum, tree built and folded in parallel: nodes live at heap indices (root 1, children 2h and 2h+1),
+// one level per barrier on the way down (split) and up (left + right).  n <= SQK_HEAP_MAX_N.
+template <class Term>
+__device__ double stats_pairwise_heap(Term term, int n, StatsShared &sh)
+{
+    const int tid = threadIdx.x;
+    for (int h = tid; h < SQK_HEAP_NODES; h += SQK_STATS_THREADS) sh.hp_len[h] = 0;
+    __syncthreads();
+    if (tid == 0) { sh.hp_off[1] = 0; sh.hp_len[1] = n; }
+    __syncthreads();
+    int depth = 0;          // deepest level that holds nodes
+    for (int d = 0; (2 << d) < SQK_HEAP_NODES; d++) {
+        int split = 0;
+        for (int h = (1 << d) + tid; h < (2 << d); h += SQK_STATS_THREADS) {
+            const int len = sh.hp_len[h];
+            if (len > 128) {
+                const int off = sh.hp_off[h];
+                int half = len / 2;
+                half -= half % 8;
+                sh.hp_off[2 * h] = off; sh.hp_len[2 * h] = half;
+                sh.hp_off[2 * h + 1] = off + half; sh.hp_len[2 * h + 1] = len - half;
+                split = 1;
+            }
+        }
+        if (!__syncthreads_or(split)) break;
+        depth = d + 1;
+    }
+    // leaves: nodes with 0 < len <= 128 (they sit on the last two levels); 8-lane teams, warps stay converged
+    const int team = tid >> 3, k = tid & 7;
+    const int first = depth > 0 ? (1 << (depth - 1)) : 1, last = (2 << depth);
+    for (int h0 = first; h0 < last; h0 += SQK_STATS_TEAMS) {
+        const int h = h0 + team;
+        const int len = h < last ? sh.hp_len[h] : 0;
+        const bool leaf = len > 0 && len <= 128;
+        // every team runs the shuffles; non-leaves sum a dummy 8-element leaf at offset 0 when n >= 8
+        const int use_off = leaf ? sh.hp_off[h] : 0;
+        const int use_len = leaf ? len : (n >= 8 ? 8 : n);
+        const double v = stats_leaf_sum(term, use_off, use_len, k);
+        if (leaf && k == 0) sh.hp_sum[h] = v;
+    }
+    __syncthreads();
+    for (int d = depth - 1; d >= 0; d--) {
+        for (int h = (1 << d) + tid; h < (2 << d); h += SQK_STATS_THREADS)
+            if (sh.hp_len[h] > 128) sh.hp_sum[h] = __dadd_rn(sh.hp_sum[2 * h], sh.hp_sum[2 * h + 1]);
+        __syncthreads();
+    }
+    const double r = sh.hp_sum[1];
+    __syncthreads();
+    return r;
+}
+
+template <class Term>
+__device__ __forceinline__ double stats_sum(Term term, int n, StatsShared &sh)
+{
+    return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap(term, n, sh) : stats_pairwise(term, n, sh);
+}
+
+// ---- order statistics from a direct histogram of the raw values (window of <= SQK_HIST_BINS values) ----
+// After stats_histogram, sh.hist[b] = number of staged samples with value <= base + b (inclusive prefix).
+__device__ void stats_histogram(const int16_t *stage, int n, int base, int nbins, StatsShared &sh)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < SQK_HIST_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SQK_STATS_THREADS) atomicAdd(&sh.hist[(int)stage[i] - base], 1u);
+    __syncthreads();
+    constexpr int PER = SQK_HIST_BINS / SQK_STATS_THREADS;      // 16 consecutive bins per thread
+    uint32_t loc[PER], run = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { run += sh.hist[tid * PER + q]; loc[q] = run; }
+    uint32_t incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) sh.scan_part[warp] = incl;
+    __syncthreads();
+    uint32_t before = incl - run;
+    for (int w = 0; w < warp; w++) before += sh.scan_part[w];
+#pragma unroll
+    for (int q = 0; q < PER; q++) sh.hist[tid * PER + q] = before + loc[q];
+    __syncthreads();
+    (void)nbins;
+}
+
+// smallest bin b with prefix[b] > rank  (rank-th smallest value = base + b)
+__device__ __forceinline__ int stats_hist_select(const StatsShared &sh, int nbins, int rank)
+{
+    int lo = 0, hi = nbins - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sh.hist[mid] > (uint32_t)rank) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// number of staged samples v with |2v - med2| <= D
+__device__ __forceinline__ int stats_hist_within(const StatsShared &sh, int base, int nbins, int med2, int D)
+{
+    // v >= ceil((med2 - D) / 2),  v <= floor((med2 + D) / 2)   (floor division on possibly negative numbers)
+    const int a = med2 - D, b = med2 + D;
+    int vlo = (a >= 0) ? (a + 1) / 2 : -((-a) / 2);
+    int vhi = (b >= 0) ? b / 2 : -((-b + 1) / 2);
+    int ilo = vlo - base, ihi = vhi - base;
+    if (ihi >= nbins) ihi = nbins - 1;
+    if (ilo < 0) ilo = 0;
+    if (ihi < ilo) return 0;
+    return (int)(sh.hist[ihi] - (ilo > 0 ? sh.hist[ilo - 1] : 0u));
+}
+
+// rank-th smallest doubled distance |2v - med2|
+__device__ __forceinline__ int stats_hist_mad(const StatsShared &sh, int base, int nbins, int med2, int rank)
+{
+    int lo = 0, hi = 4 * SQK_HIST_BINS;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (stats_hist_within(sh, base, nbins, med2, mid) > rank) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// rank-th smallest (0-based) of key(i), i < n, keys < 512*256.  Two-pass radix select (wide windows).
 template <class KeyFn>
 __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
 {
@@ -142,7 +270,7 @@ __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
     uint32_t prefix = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        for (int b = tid; b < SQK_HIST_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
+        for (int b = tid; b < SQK_RADIX_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
         __syncthreads();
         for (int i = tid; i < n; i += SQK_STATS_THREADS) {
             const uint32_t kv = key(i);
@@ -151,7 +279,7 @@ __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
         }
         __syncthreads();
         if (tid < 32) {
-            const int per = SQK_HIST_BINS / 32;
+            const int per = SQK_RADIX_BINS / 32;
             uint32_t mine = 0;
             for (int b = 0; b < per; b++) mine += sh.hist[tid * per + b];
             uint32_t incl = mine;
@@ -293,16 +421,16 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 // integer samples: the sum is exact in any order
                 const double mean = __ddiv_rn((double)tot_sum, (double)n);
                 auto sq = [stage, mean](int q) -> double { const double d = __dsub_rn((double)stage[q], mean); return __dmul_rn(d, d); };
-                sd = __dsqrt_rn(__ddiv_rn(stats_pairwise(sq, n, sh), (double)n));
+                sd = __dsqrt_rn(__ddiv_rn(stats_sum(sq, n, sh), (double)n));
             } else {
                 // pA samples are not integers: np.std's mean is itself a pairwise sum
                 auto val = [stage, pa_off, pa_unit](int q) -> double { return sqk_pa_value((int)stage[q], pa_off, pa_unit); };
-                const double mean = __ddiv_rn(stats_pairwise(val, n, sh), (double)n);
+                const double mean = __ddiv_rn(stats_sum(val, n, sh), (double)n);
                 auto sq = [stage, pa_off, pa_unit, mean](int q) -> double {
                     const double d = __dsub_rn(sqk_pa_value((int)stage[q], pa_off, pa_unit), mean);
                     return __dmul_rn(d, d);
                 };
-                sd = __dsqrt_rn(__ddiv_rn(stats_pairwise(sq, n, sh), (double)n));
+                sd = __dsqrt_rn(__ddiv_rn(stats_sum(sq, n, sh), (double)n));
             }
             if (a.mode == SQK_STATS_ZSCALE) {
                 if (sd == 0.0) sd = 1.0;          // sklearn _handle_zeros_in_scale
@@ -310,9 +438,15 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
             }
         }
         if (n > 0 && (a.mode == SQK_STATS_MEDMAD || a.mode == SQK_STATS_SEGMENTER)) {
+            const int nbins = out_hi - out_lo + 1;
+            const bool direct = nbins <= SQK_HIST_BINS;      // narrow window: one histogram serves median and MAD
             auto key_x = [stage](int q) -> uint32_t { return (uint32_t)((int)stage[q] + 32768); };
             int lo_v, hi_v;   // the two middle order statistics (equal for odd n)
-            if (n & 1) {
+            if (direct) {
+                stats_histogram(stage, n, out_lo, nbins, sh);
+                lo_v = out_lo + stats_hist_select(sh, nbins, (n - 1) / 2);
+                hi_v = (n & 1) ? lo_v : out_lo + stats_hist_select(sh, nbins, n / 2);
+            } else if (n & 1) {
                 lo_v = hi_v = (int)stats_select(key_x, n, (n - 1) / 2, sh) - 32768;
             } else {
                 lo_v = (int)stats_select(key_x, n, n / 2 - 1, sh) - 32768;
@@ -326,7 +460,11 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                     return (uint32_t)(d < 0 ? -d : d);
                 };
                 double mad;
-                if (n & 1) {
+                if (direct) {
+                    const int d0 = stats_hist_mad(sh, out_lo, nbins, med2, (n - 1) / 2);
+                    const int d1 = (n & 1) ? d0 : stats_hist_mad(sh, out_lo, nbins, med2, n / 2);
+                    mad = (double)(d0 + d1) * 0.25;
+                } else if (n & 1) {
                     mad = (double)stats_select(key_d, n, (n - 1) / 2, sh) * 0.5;
                 } else {
                     const uint32_t d0 = stats_select(key_d, n, n / 2 - 1, sh);

@@ -67,6 +67,55 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) ub_dtw_cost(int steps, const 
 }
 
 template <typename T, int K, int L>
+__global__ void __launch_bounds__(SQK_DTW_THREADS) ub_dtw2(int steps, const double *model, T *sink)
+{
+    constexpr int G = 32 / L, RC = 16 * L;
+    __shared__ __align__(16) T ring_all[SQK_DTW_WARPS * G * RC];
+    const int lane = threadIdx.x & 31, l = lane % L, g = lane / L;
+    T *ring = ring_all + ((threadIdx.x >> 5) * G + g) * RC;
+    for (int q = l; q < RC; q += L) ring[q] = (T)(((q * 2654435761u) >> 20) & 1023) * (T)(1.0 / 256) - (T)2;
+    __syncwarp();
+    T x[K], c[K];
+    int s[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { x[k] = (T)model[(l * K + k) % 80]; c[k] = DtwNum<T>::inf(); s[k] = 0; }
+    T botA = DtwNum<T>::inf(), botB = DtwNum<T>::inf(), prev_c = (l == 0) ? (T)0 : DtwNum<T>::inf(), best = DtwNum<T>::inf();
+    int botA_s = 0, botB_s = 0, prev_s = 0, best_j = -1, best_s = -1;
+    const int n = (l == L - 1) ? steps : 0;
+    for (int tp = 0; tp < steps / 2; tp++)
+        dtw_step2<T, K, L, false>(c, s, x, ring, l, false, tp, n, botA, botA_s, botB, botB_s, prev_c, prev_s, best, best_j, best_s);
+    T acc = best + (T)best_j + (T)best_s;
+#pragma unroll
+    for (int k = 0; k < K; k++) acc += c[k] + (T)s[k];
+    if (acc == (T)123456.789) sink[0] = acc;
+}
+
+template <typename T, int K, int L>
+static void run_dtw2(const char *prec, int sms, const double *d_model, void *d_sink)
+{
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ub_dtw2<T, K, L>, SQK_DTW_THREADS, 0));
+    const int grid = sms * occ, steps = 8192;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    ub_dtw2<T, K, L><<<grid, SQK_DTW_THREADS>>>(256, d_model, (T *)d_sink);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(a));
+        ub_dtw2<T, K, L><<<grid, SQK_DTW_THREADS>>>(steps, d_model, (T *)d_sink);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double cells = (double)grid * SQK_DTW_THREADS * K * steps;
+    printf("{\"bench\": \"dtw_step2\", \"precision\": \"%s\", \"K\": %d, \"L\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, "
+           "\"cells_per_s\": %.4e}\n", prec, K, L, occ, best_ms, cells / (best_ms * 1e-3));
+    fflush(stdout);
+}
+
+template <typename T, int K, int L>
 static void run_dtw_cost(const char *prec, int sms, const double *d_model, void *d_sink)
 {
     int occ = 0;
@@ -189,6 +238,10 @@ int main(int argc, char **argv)
     run_dtw<double, 5, 16>("fp64", sms, d_model, d_sink);
     run_dtw<float, 20, 4>("fp32", sms, d_model, d_sink);
     run_dtw<float, 10, 8>("fp32", sms, d_model, d_sink);
+    run_dtw2<double, 10, 8>("fp64", sms, d_model, d_sink);
+    run_dtw2<double, 20, 4>("fp64", sms, d_model, d_sink);
+    run_dtw2<double, 5, 16>("fp64", sms, d_model, d_sink);
+    run_dtw2<float, 10, 8>("fp32", sms, d_model, d_sink);
     run_dtw_cost<double, 10, 8>("fp64", sms, d_model, d_sink);
     run_dtw_cost<double, 20, 4>("fp64", sms, d_model, d_sink);
     if (full) {
