@@ -46,18 +46,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks + throttle reasons, one sample every 50 ms.  The sampler runs from before the warm-up
+    (nvidia-smi needs a moment to start); mark()/unmark() bracket the timed region and summary() only uses
+    the samples that arrived inside it."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -67,11 +70,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
+
+    def unmark(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.25)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -79,19 +87,29 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0])); mx.append(float(r[1]))
+                except Exception:
+                    continue
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30)]
+        sm, mx, reasons = digest(inside)
+        sm_all, mx_all, reasons_all = digest(self.rows)
+        if not sm_all:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        use = sm if sm else sm_all
+        return {"sm_mhz": statistics.median(use), "sm_max_mhz": max(mx_all), "reasons": sorted(reasons if sm else reasons_all),
+                "samples": len(sm), "samples_incl_warmup": len(sm_all), "sm_mhz_min_incl_warmup": min(sm_all),
+                "reasons_incl_warmup": sorted(reasons_all)}
 
 
 def cpu_reference_rate(signals, offsets, motif, threads: int, target_s: float):
@@ -223,19 +241,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        gathered = step()
-    barrier()
-    ctx.enable_timing(True)
-    ctx.timing(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            gathered = step()
         barrier()
+        ctx.enable_timing(True)
+        ctx.timing(reset=True)
+        barrier()
+        clocks.mark()
         ev0.record()
         for _ in range(args.steps):
             gathered = step()
         ev1.record()
         barrier()
+        clocks.unmark()
     ms = ev0.elapsed_time(ev1)
     kt = ctx.timing(reset=True)
     ctx.enable_timing(False)

@@ -250,3 +250,40 @@ def test_bench_size_properties(ctx):
     assert_hits_equal(h[idx], want, kept[idx], kept_w, "bench-size subsample")
     # planted motifs are found: at least 45 % of reads have a hit with a small distance
     assert (h["dist"] < 25).mean() > 0.4
+
+
+def test_very_long_reads_use_global_staging(ctx):
+    """Reads longer than the shared-memory staging window of the stats kernel (~113k samples) take the global
+    scratch path; the DTW itself streams any length."""
+    motif = synth.make_motif()
+    sig, off = synth.ragged_reads_np([300_000, 120_000, 5000, 250_001], motif)
+    for scale in ("zscale", "medmad"):
+        want, kept_w = oracle_hits(sig, off, motif, scale)
+        hits, kept = ctx.motifseq(sig, off, motif, scale=scale)
+        assert_hits_equal(hits[:, 0], want, kept, kept_w, f"long/{scale}")
+    segs, nsegs = ctx.segmenter(sig, off, sqk.SegConfig(max_segs=64))
+    want_s, want_n = oracle.segmenter_batch(sig, off, oracle.SegCfg(), 0, 900, 0, 64)
+    assert np.array_equal(nsegs, want_n)
+    for r in range(nsegs.size):
+        assert np.array_equal(segs[r, :nsegs[r]], want_s[r, :want_n[r]])
+
+
+def test_argument_errors_are_reported_not_crashed(ctx):
+    motif = synth.make_motif()
+    sig, off, _ = synth.motifseq_reads_np(4, 500, motif)
+    hits, kept = ctx.motifseq(sig[:0], np.zeros(1, dtype=np.int64), motif)          # zero reads is fine
+    assert hits.shape == (0, 1)
+    with pytest.raises(sqk.SqkError) as ei:
+        ctx.motifseq(sig, off[::-1].copy(), motif)                                   # offsets not monotone
+    assert ei.value.code == -1
+    with pytest.raises(sqk.SqkError) as ei:
+        ctx.motifseq(sig, off, np.zeros(2000))                                       # motif longer than supported
+    assert ei.value.code == -4
+    with pytest.raises(sqk.SqkError):
+        ctx.segmenter(sig, off, sqk.SegConfig(corrector=-1))
+    with pytest.raises(sqk.SqkError):
+        ctx.segmenter(sig, off, sqk.SegConfig(max_segs=0))
+    # the context is still usable afterwards
+    want, _ = oracle_hits(sig, off, motif, "zscale")
+    hits, _ = ctx.motifseq(sig, off, motif, scale="zscale")
+    assert_hits_equal(hits[:, 0], want, what="after errors")
