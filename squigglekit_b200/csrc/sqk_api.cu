@@ -148,7 +148,7 @@ struct sqk_ctx {
     std::vector<cudaEvent_t> pool;
     sqk_timing acc{};
     int force_lanes = 0;
-    int stats_smem_set = -1;
+    int stats_smem_set32 = -1, stats_smem_set128 = -1;
 };
 
 struct Guard {   // make the ctx device current for the duration of a call
@@ -299,44 +299,60 @@ struct View {                 // a set of reads resident on the device
 
 static inline int clamp_lim(int v) { return v < -40000 ? -40000 : (v > 40000 ? 40000 : v); }   // samples are int16
 
+template <int NT>
+static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, int *smem_set)
+{
+    constexpr int GROUPS = SQK_STATS_THREADS / NT;
+    const size_t fixed = (sizeof(StatsShared) + 15) & ~(size_t)15;
+    // staging capacity per group: the longest read if it fits (2 bytes/sample)
+    const int64_t budget = ((int64_t)c->smem_optin - 1024) / GROUPS - (int64_t)fixed;
+    int64_t cap_max = budget / 2;
+    cap_max &= ~127ll;
+    int64_t cap = (std::max<int64_t>(v.max_len, 8) + 127) & ~127ll;
+    if (cap > cap_max) cap = cap_max;
+    const size_t group_bytes = fixed + (size_t)cap * 2;
+    const int dyn = (int)(group_bytes * GROUPS);
+    if (dyn > *smem_set) {
+        CU(cudaFuncSetAttribute(sqk_stats_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        *smem_set = dyn;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel<NT>, SQK_STATS_THREADS, dyn));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (v.n_reads + GROUPS - 1) / GROUPS;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->n_sms * per_sm));
+    a.cap = (int)cap; a.gstage = nullptr; a.gstage_stride = 0;
+    if (v.max_len > cap && a.mode != SQK_STATS_NONE) {
+        const int64_t stride = (v.max_len + 7) & ~7ll;
+        TRY(ensure(s.gstage, (size_t)grid * GROUPS * stride * sizeof(int16_t)));
+        a.gstage = (int16_t *)s.gstage.p; a.gstage_stride = stride;
+    }
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_STATS, st, &eb));
+    sqk_stats_kernel<NT><<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
 static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
                         double std_scale, int32_t *d_nkept, const double *d_pa_off = nullptr,
                         const double *d_pa_scale = nullptr)
 {
     lo = clamp_lim(lo); hi = clamp_lim(hi);
     TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
-    const int static_smem = (int)sizeof(StatsShared) + 64;
-    const int cap_max = (c->smem_optin - static_smem - 1024) / 2;
-    int64_t cap = std::min<int64_t>(std::max<int64_t>(v.max_len, 8), cap_max);
-    cap = (cap + 7) & ~7ll;
-    const int dyn = (int)cap * 2;
-    if (dyn > c->stats_smem_set) {
-        CU(cudaFuncSetAttribute(sqk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        c->stats_smem_set = dyn;
-    }
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel, SQK_STATS_THREADS, dyn));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * per_sm));
-
     StatsArgs a{};
     a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
     a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = v.n_reads;
     a.stats = (ReadStats *)s.stats.p; a.n_kept_out = d_nkept;
     a.mode = mode; a.lo = lo; a.hi = hi; a.num = num; a.std_scale = std_scale;
     a.pa_offset = d_pa_off; a.pa_scale = d_pa_scale;
-    a.cap = (int)cap; a.gstage = nullptr; a.gstage_stride = 0;
-    if (v.max_len > cap && mode != SQK_STATS_NONE) {
-        const int64_t stride = (v.max_len + 7) & ~7ll;
-        TRY(ensure(s.gstage, (size_t)grid * stride * sizeof(int16_t)));
-        a.gstage = (int16_t *)s.gstage.p; a.gstage_stride = stride;
-    }
-    cudaEvent_t eb;
-    TRY(tick(c, SQK_K_STATS, st, &eb));
-    sqk_stats_kernel<<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
-    CU(cudaGetLastError());
-    TRY(tock(eb, st));
-    return SQK_OK;
+    // one CTA per read; the warp-per-read form (SQK_STATS_NT=32, reads <= 8192 samples) is kept for experiments
+    static int force_nt = -1;
+    if (force_nt < 0) { const char *e = getenv("SQK_STATS_NT"); force_nt = e ? atoi(e) : 0; }
+    const bool warp_per_read = force_nt == 32 && v.max_len <= SQK_HEAP_MAX_N;
+    return warp_per_read ? launch_stats_nt<32>(c, s, st, a, v, &c->stats_smem_set32)
+                         : launch_stats_nt<128>(c, s, st, a, v, &c->stats_smem_set128);
 }
 
 static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_out, sqk_dtw_launcher *fn)
@@ -431,15 +447,17 @@ static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v
 {
     if (v.n_reads == 0) return SQK_OK;
     if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
-    TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr, d_pa_off, d_pa_scale));
+    const double fm = std::ceil((double)p->window * p->stall_len);
+    const int first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
+    TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr, d_pa_off,
+                     d_pa_scale));
     FsmArgs a{};
     a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
     a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
     a.stats = (const ReadStats *)s.stats.p;
     a.num = p->num;
     a.error = p->error; a.corrector = p->corrector; a.window = p->window; a.seg_dist = p->seg_dist;
-    const double fm = std::ceil((double)p->window * p->stall_len);
-    a.first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
+    a.first_min = first_min;
     a.max_segs = p->max_segs; a.segs = d_segs; a.n_segs = d_nsegs;
     const unsigned grid = (unsigned)((v.n_reads + SQK_FSM_THREADS - 1) / SQK_FSM_THREADS);
     cudaEvent_t eb;

@@ -1,31 +1,37 @@
 // sqk_stats.cuh -- K1: per-read outlier compaction + the statistics that normalisation
 // (MotifSeq.py:186-200) and get_segs (segmenter.py:407-414) need, bit-identical to numpy.
 //
-// One CTA per read (persistent, strided over reads).  The read is fetched from HBM ONCE with
-// 16-byte streaming loads, filtered  lo < s < hi  (scale_outliers, MotifSeq.py:317-324 /
-// segmenter.py:311-318) with a ballot-free popc prefix, and the survivors are parked as int16 in
-// shared memory (or, for reads longer than the shared-memory window, in a global scratch row);
-// every later pass runs from that copy.
+// A read is owned by a group of NT threads: NT = 128 (one CTA per read) by default; NT = 32 (one warp per
+// read, four reads per CTA, only __syncwarp between phases) exists for experiments (SQK_STATS_NT=32) and
+// measured slower on B200: fewer resident warps per SM than the CTA-per-read form.  The
+// read is fetched from HBM ONCE with 16-byte streaming loads, filtered  lo < s < hi  (scale_outliers,
+// MotifSeq.py:317-324 / segmenter.py:311-318) with a popc prefix, and the survivors are parked as int16
+// in shared memory (reads longer than the shared-memory window: a global scratch row); every later
+// pass runs from that copy.
 //
 //   zscale    mean = sum/n (integer sum: exact, order-free);  sd = sqrt(S/n) with S = the sum of
-//             fl(fl(x-mean)^2) taken in numpy's pairwise order (8-lane teams own the <=128-element
-//             leaves: one lane per strided accumulator, xor-butterfly = numpy's fold; the
-//             leaves are combined by a depth stack in DFS order) -> same bits as
-//             sklearn.preprocessing.scale / np.std.
-//   medmad    median and MAD by two-pass radix select on integer keys (x, then |2x - 2med|):
-//             exact, including the x.5 medians of even-length reads.
-//   segmenter median (select) + sd (pairwise) -> integer thresholds equivalent to bot < x < top.
+//             fl(fl(x-mean)^2) taken in numpy's pairwise order: 8-lane teams own the <=128-element
+//             leaves (one lane per strided accumulator, xor-butterfly = numpy's fold); the split tree is
+//             built and folded level by level at heap indices (n <= 8192) or walked depth-first (longer)
+//             -> same bits as sklearn.preprocessing.scale / np.std.
+//   medmad    median and MAD from ONE shared-memory histogram of the raw values + prefix scan when the
+//             outlier window spans <= 2048 values (MAD by binary search on count(|2v - 2med| <= D)),
+//             else by two-pass radix select: exact, including the x.5 medians of even-length reads.
+//   segmenter median + sd -> thresholds -> integer window seg_lo <= x <= seg_hi equivalent to
+//             bot < x < top; pA mode evaluates convert_to_pA_numpy + np.round per sample with numpy's
+//             roundings (monotone in the raw value, so every window stays an integer window).
+//             The state machine itself is K3 (sqk_segmenter.cuh).  (A variant that ran get_segs here, on a bit
+//             mask of the staged samples with popc run-skipping, was measured and dropped: one thread per read
+//             walking ~300 candidate segments is slower than K3's 32 reads per warp.)
 #pragma once
 #include "sqk_common.cuh"
 
-#define SQK_STATS_THREADS 128
-#define SQK_STATS_WARPS (SQK_STATS_THREADS / 32)
-#define SQK_STATS_TEAMS (SQK_STATS_THREADS / 8)
+#define SQK_STATS_THREADS 128       // CTA size; a read is owned by NT = 32 or 128 of them
 #define SQK_LEAF_BATCH 64
 #define SQK_TREE_DEPTH 48
 #define SQK_HIST_BINS 2048          // direct histogram when the outlier window spans <= 2048 raw values
 #define SQK_RADIX_BINS 512          // fallback two-pass radix select (9 + 8 bits)
-#define SQK_HEAP_NODES 512          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
+#define SQK_HEAP_NODES 256          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
 #define SQK_HEAP_MAX_N 8192
 
 enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3 };
@@ -41,27 +47,44 @@ struct StatsArgs {
     double std_scale;
     const double *pa_offset;  // segmenter pA mode: per-read calibration, indexable by absolute read id (or null)
     const double *pa_scale;   //   pA = round((d + pa_offset) * pa_scale, 2)
-    int cap;                  // shared-memory staging capacity (samples)
+    int cap;                  // shared-memory staging capacity per group (samples, multiple of 64)
     int16_t *gstage;          // global staging rows for reads longer than cap (or null)
     int64_t gstage_stride;
 };
 
 struct StatsShared {
-    unsigned long long sum_part[SQK_STATS_WARPS];
-    int warp_tot[SQK_STATS_WARPS];
-    uint32_t hist[SQK_HIST_BINS];
+    union {                                           // the three users never overlap in time
+        uint32_t hist[SQK_HIST_BINS];                 // median / MAD histogram, then its prefix sums
+        struct {
+            int off[SQK_HEAP_NODES], len[SQK_HEAP_NODES];
+            double sum[SQK_HEAP_NODES];
+        } hp;                                         // heap-indexed pairwise tree (n <= SQK_HEAP_MAX_N)
+        struct {
+            int st_off[SQK_TREE_DEPTH], st_len[SQK_TREE_DEPTH], st_dep[SQK_TREE_DEPTH];
+            int lf_off[SQK_LEAF_BATCH], lf_len[SQK_LEAF_BATCH], lf_dep[SQK_LEAF_BATCH];
+            double lf_sum[SQK_LEAF_BATCH];
+            double cs_val[SQK_TREE_DEPTH];
+            int cs_dep[SQK_TREE_DEPTH];
+            int sp, csp, nleaf;
+        } wk;                                         // serial depth-first walk (longer reads)
+    };
+    unsigned long long sum_part[4];
+    int warp_tot[4];
+    uint32_t scan_part[4];
     uint32_t sel[2];
-    int st_off[SQK_TREE_DEPTH], st_len[SQK_TREE_DEPTH], st_dep[SQK_TREE_DEPTH];
-    int lf_off[SQK_LEAF_BATCH], lf_len[SQK_LEAF_BATCH], lf_dep[SQK_LEAF_BATCH];
-    double lf_sum[SQK_LEAF_BATCH];
-    double cs_val[SQK_TREE_DEPTH];
-    int cs_dep[SQK_TREE_DEPTH];
-    int sp, csp, nleaf;
     double result;
-    int hp_off[SQK_HEAP_NODES], hp_len[SQK_HEAP_NODES];
-    double hp_sum[SQK_HEAP_NODES];
-    uint32_t scan_part[SQK_STATS_WARPS];
 };
+
+// barrier over the NT threads that own a read
+template <int NT> __device__ __forceinline__ void stats_sync()
+{
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+template <int NT> __device__ __forceinline__ int stats_sync_or(int pred)
+{
+    if (NT == 32) return __any_sync(SQK_FULL_MASK, pred);
+    return __syncthreads_or(pred);
+}
 
 // numpy pairwise leaf (n <= 128) over term(i), evaluated by an 8-lane team (lane k = accumulator k).
 template <class Term>
@@ -82,148 +105,155 @@ __device__ __forceinline__ double stats_leaf_sum(Term term, int off, int len, in
     return r;
 }
 
-// np.sum over term(0..n-1) in numpy's pairwise order; result valid in every thread.
-template <class Term>
+// np.sum over term(0..n-1) in numpy's pairwise order, any n: serial depth-first walk by one thread, leaves in
+// batches by the teams, leaf sums folded with a depth stack.  Result valid in every thread of the group.
+template <int NT, class Term>
 __device__ double stats_pairwise(Term term, int n, StatsShared &sh)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % NT;
+    constexpr int TEAMS = NT / 8;
     if (tid == 0) {
-        sh.st_off[0] = 0; sh.st_len[0] = n; sh.st_dep[0] = 0;
-        sh.sp = 1; sh.csp = 0;
+        sh.wk.st_off[0] = 0; sh.wk.st_len[0] = n; sh.wk.st_dep[0] = 0;
+        sh.wk.sp = 1; sh.wk.csp = 0;
     }
-    __syncthreads();
+    stats_sync<NT>();
     for (;;) {
         if (tid == 0) {
             // resume the depth-first walk: emit the next batch of leaves in numpy's evaluation order
-            int sp = sh.sp, nl = 0;
+            int sp = sh.wk.sp, nl = 0;
             while (sp > 0 && nl < SQK_LEAF_BATCH) {
                 sp--;
-                const int off = sh.st_off[sp], len = sh.st_len[sp], dep = sh.st_dep[sp];
+                const int off = sh.wk.st_off[sp], len = sh.wk.st_len[sp], dep = sh.wk.st_dep[sp];
                 if (len <= 128) {
-                    sh.lf_off[nl] = off; sh.lf_len[nl] = len; sh.lf_dep[nl] = dep; nl++;
+                    sh.wk.lf_off[nl] = off; sh.wk.lf_len[nl] = len; sh.wk.lf_dep[nl] = dep; nl++;
                 } else {
                     int h = len / 2;
                     h -= h % 8;
-                    sh.st_off[sp] = off + h; sh.st_len[sp] = len - h; sh.st_dep[sp] = dep + 1; sp++;   // right, popped later
-                    sh.st_off[sp] = off; sh.st_len[sp] = h; sh.st_dep[sp] = dep + 1; sp++;             // left, popped next
+                    sh.wk.st_off[sp] = off + h; sh.wk.st_len[sp] = len - h; sh.wk.st_dep[sp] = dep + 1; sp++;   // right, popped later
+                    sh.wk.st_off[sp] = off; sh.wk.st_len[sp] = h; sh.wk.st_dep[sp] = dep + 1; sp++;             // left, popped next
                 }
             }
-            sh.sp = sp; sh.nleaf = nl;
+            sh.wk.sp = sp; sh.wk.nleaf = nl;
         }
-        __syncthreads();
-        const int nl = sh.nleaf;
+        stats_sync<NT>();
+        const int nl = sh.wk.nleaf;
         if (nl == 0) break;
         const int team = tid >> 3, k = tid & 7;
-        for (int q = team; q < ((nl + SQK_STATS_TEAMS - 1) / SQK_STATS_TEAMS) * SQK_STATS_TEAMS; q += SQK_STATS_TEAMS) {
+        for (int q = team; q < ((nl + TEAMS - 1) / TEAMS) * TEAMS; q += TEAMS) {
             // whole warps stay converged for the shuffles; surplus teams redo the last leaf
             const int qq = q < nl ? q : nl - 1;
-            const double s = stats_leaf_sum(term, sh.lf_off[qq], sh.lf_len[qq], k);
-            if (q < nl && k == 0) sh.lf_sum[q] = s;
+            const double s = stats_leaf_sum(term, sh.wk.lf_off[qq], sh.wk.lf_len[qq], k);
+            if (q < nl && k == 0) sh.wk.lf_sum[q] = s;
         }
-        __syncthreads();
+        stats_sync<NT>();
         if (tid == 0) {
-            int csp = sh.csp;
+            int csp = sh.wk.csp;
             for (int q = 0; q < nl; q++) {
-                double v = sh.lf_sum[q];
-                int dep = sh.lf_dep[q];
-                while (csp > 0 && sh.cs_dep[csp - 1] == dep) {   // sibling on the stack: left + right
-                    v = __dadd_rn(sh.cs_val[csp - 1], v);
+                double v = sh.wk.lf_sum[q];
+                int dep = sh.wk.lf_dep[q];
+                while (csp > 0 && sh.wk.cs_dep[csp - 1] == dep) {   // sibling on the stack: left + right
+                    v = __dadd_rn(sh.wk.cs_val[csp - 1], v);
                     dep--; csp--;
                 }
-                sh.cs_val[csp] = v; sh.cs_dep[csp] = dep; csp++;
+                sh.wk.cs_val[csp] = v; sh.wk.cs_dep[csp] = dep; csp++;
             }
-            sh.csp = csp;
-            if (sh.sp == 0) sh.result = sh.cs_val[0];
+            sh.wk.csp = csp;
+            if (sh.wk.sp == 0) sh.result = sh.wk.cs_val[0];
         }
-        __syncthreads();
+        stats_sync<NT>();
     }
     return sh.result;
 }
 
 // Same sum, tree built and folded in parallel: nodes live at heap indices (root 1, children 2h and 2h+1),
-// one level per barrier on the way down (split) and up (left + right).  n <= SQK_HEAP_MAX_N.
-template <class Term>
+// one level per barrier on the way down (split) and up (left + right).  n <= SQK_HEAP_MAX_N: depth <= 7.
+template <int NT, class Term>
 __device__ double stats_pairwise_heap(Term term, int n, StatsShared &sh)
 {
-    const int tid = threadIdx.x;
-    for (int h = tid; h < SQK_HEAP_NODES; h += SQK_STATS_THREADS) sh.hp_len[h] = 0;
-    __syncthreads();
-    if (tid == 0) { sh.hp_off[1] = 0; sh.hp_len[1] = n; }
-    __syncthreads();
+    const int tid = threadIdx.x % NT;
+    constexpr int TEAMS = NT / 8;
+    for (int h = tid; h < SQK_HEAP_NODES; h += NT) sh.hp.len[h] = 0;
+    stats_sync<NT>();
+    if (tid == 0) { sh.hp.off[1] = 0; sh.hp.len[1] = n; }
+    stats_sync<NT>();
     int depth = 0;          // deepest level that holds nodes
-    for (int d = 0; (2 << d) < SQK_HEAP_NODES; d++) {
+    for (int d = 0; (4 << d) <= SQK_HEAP_NODES; d++) {
         int split = 0;
-        for (int h = (1 << d) + tid; h < (2 << d); h += SQK_STATS_THREADS) {
-            const int len = sh.hp_len[h];
+        for (int h = (1 << d) + tid; h < (2 << d); h += NT) {
+            const int len = sh.hp.len[h];
             if (len > 128) {
-                const int off = sh.hp_off[h];
+                const int off = sh.hp.off[h];
                 int half = len / 2;
                 half -= half % 8;
-                sh.hp_off[2 * h] = off; sh.hp_len[2 * h] = half;
-                sh.hp_off[2 * h + 1] = off + half; sh.hp_len[2 * h + 1] = len - half;
+                sh.hp.off[2 * h] = off; sh.hp.len[2 * h] = half;
+                sh.hp.off[2 * h + 1] = off + half; sh.hp.len[2 * h + 1] = len - half;
                 split = 1;
             }
         }
-        if (!__syncthreads_or(split)) break;
+        if (!stats_sync_or<NT>(split)) break;
         depth = d + 1;
     }
     // leaves: nodes with 0 < len <= 128 (they sit on the last two levels); 8-lane teams, warps stay converged
     const int team = tid >> 3, k = tid & 7;
     const int first = depth > 0 ? (1 << (depth - 1)) : 1, last = (2 << depth);
-    for (int h0 = first; h0 < last; h0 += SQK_STATS_TEAMS) {
+    for (int h0 = first; h0 < last; h0 += TEAMS) {
         const int h = h0 + team;
-        const int len = h < last ? sh.hp_len[h] : 0;
+        const int len = h < last ? sh.hp.len[h] : 0;
         const bool leaf = len > 0 && len <= 128;
-        // every team runs the shuffles; non-leaves sum a dummy 8-element leaf at offset 0 when n >= 8
-        const int use_off = leaf ? sh.hp_off[h] : 0;
+        // every team runs the shuffles; non-leaves sum a dummy leaf at offset 0
+        const int use_off = leaf ? sh.hp.off[h] : 0;
         const int use_len = leaf ? len : (n >= 8 ? 8 : n);
         const double v = stats_leaf_sum(term, use_off, use_len, k);
-        if (leaf && k == 0) sh.hp_sum[h] = v;
+        if (leaf && k == 0) sh.hp.sum[h] = v;
     }
-    __syncthreads();
+    stats_sync<NT>();
     for (int d = depth - 1; d >= 0; d--) {
-        for (int h = (1 << d) + tid; h < (2 << d); h += SQK_STATS_THREADS)
-            if (sh.hp_len[h] > 128) sh.hp_sum[h] = __dadd_rn(sh.hp_sum[2 * h], sh.hp_sum[2 * h + 1]);
-        __syncthreads();
+        for (int h = (1 << d) + tid; h < (2 << d); h += NT)
+            if (sh.hp.len[h] > 128) sh.hp.sum[h] = __dadd_rn(sh.hp.sum[2 * h], sh.hp.sum[2 * h + 1]);
+        stats_sync<NT>();
     }
-    const double r = sh.hp_sum[1];
-    __syncthreads();
+    const double r = sh.hp.sum[1];
+    stats_sync<NT>();
     return r;
 }
 
-template <class Term>
+template <int NT, class Term>
 __device__ __forceinline__ double stats_sum(Term term, int n, StatsShared &sh)
 {
-    return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap(term, n, sh) : stats_pairwise(term, n, sh);
+    return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap<NT>(term, n, sh) : stats_pairwise<NT>(term, n, sh);
 }
 
 // ---- order statistics from a direct histogram of the raw values (window of <= SQK_HIST_BINS values) ----
 // After stats_histogram, sh.hist[b] = number of staged samples with value <= base + b (inclusive prefix).
-__device__ void stats_histogram(const int16_t *stage, int n, int base, int nbins, StatsShared &sh)
+template <int NT>
+__device__ void stats_histogram(const int16_t *stage, int n, int base, StatsShared &sh)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int b = tid; b < SQK_HIST_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += SQK_STATS_THREADS) atomicAdd(&sh.hist[(int)stage[i] - base], 1u);
-    __syncthreads();
-    constexpr int PER = SQK_HIST_BINS / SQK_STATS_THREADS;      // 16 consecutive bins per thread
-    uint32_t loc[PER], run = 0;
-#pragma unroll
-    for (int q = 0; q < PER; q++) { run += sh.hist[tid * PER + q]; loc[q] = run; }
+    const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < SQK_HIST_BINS; b += NT) sh.hist[b] = 0;
+    stats_sync<NT>();
+    for (int i = tid; i < n; i += NT) atomicAdd(&sh.hist[(int)stage[i] - base], 1u);
+    stats_sync<NT>();
+    constexpr int PER = SQK_HIST_BINS / NT;      // consecutive bins per thread
+    uint32_t run = 0;
+    for (int q = 0; q < PER; q++) run += sh.hist[tid * PER + q];
     uint32_t incl = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
         if (lane >= d) incl += t;
     }
-    if (lane == 31) sh.scan_part[warp] = incl;
-    __syncthreads();
-    uint32_t before = incl - run;
-    for (int w = 0; w < warp; w++) before += sh.scan_part[w];
-#pragma unroll
-    for (int q = 0; q < PER; q++) sh.hist[tid * PER + q] = before + loc[q];
-    __syncthreads();
-    (void)nbins;
+    if (NT > 32) {
+        if (lane == 31) sh.scan_part[warp] = incl;
+        stats_sync<NT>();
+    }
+    uint32_t acc = incl - run;
+    if (NT > 32)
+        for (int w = 0; w < warp; w++) acc += sh.scan_part[w];
+    for (int q = 0; q < PER; q++) {
+        acc += sh.hist[tid * PER + q];
+        sh.hist[tid * PER + q] = acc;
+    }
+    stats_sync<NT>();
 }
 
 // smallest bin b with prefix[b] > rank  (rank-th smallest value = base + b)
@@ -242,8 +272,8 @@ __device__ __forceinline__ int stats_hist_within(const StatsShared &sh, int base
 {
     // v >= ceil((med2 - D) / 2),  v <= floor((med2 + D) / 2)   (floor division on possibly negative numbers)
     const int a = med2 - D, b = med2 + D;
-    int vlo = (a >= 0) ? (a + 1) / 2 : -((-a) / 2);
-    int vhi = (b >= 0) ? b / 2 : -((-b + 1) / 2);
+    const int vlo = (a >= 0) ? (a + 1) / 2 : -((-a) / 2);
+    const int vhi = (b >= 0) ? b / 2 : -((-b + 1) / 2);
     int ilo = vlo - base, ihi = vhi - base;
     if (ihi >= nbins) ihi = nbins - 1;
     if (ilo < 0) ilo = 0;
@@ -263,21 +293,21 @@ __device__ __forceinline__ int stats_hist_mad(const StatsShared &sh, int base, i
 }
 
 // rank-th smallest (0-based) of key(i), i < n, keys < 512*256.  Two-pass radix select (wide windows).
-template <class KeyFn>
+template <int NT, class KeyFn>
 __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % NT;
     uint32_t prefix = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        for (int b = tid; b < SQK_RADIX_BINS; b += SQK_STATS_THREADS) sh.hist[b] = 0;
-        __syncthreads();
-        for (int i = tid; i < n; i += SQK_STATS_THREADS) {
+        for (int b = tid; b < SQK_RADIX_BINS; b += NT) sh.hist[b] = 0;
+        stats_sync<NT>();
+        for (int i = tid; i < n; i += NT) {
             const uint32_t kv = key(i);
             if (pass == 0) atomicAdd(&sh.hist[kv >> 8], 1u);
             else if ((kv >> 8) == prefix) atomicAdd(&sh.hist[kv & 255u], 1u);
         }
-        __syncthreads();
+        stats_sync<NT>();
         if (tid < 32) {
             const int per = SQK_RADIX_BINS / 32;
             uint32_t mine = 0;
@@ -297,10 +327,10 @@ __device__ uint32_t stats_select(KeyFn key, int n, int rank, StatsShared &sh)
                 }
             }
         }
-        __syncthreads();
+        stats_sync<NT>();
         if (pass == 0) { prefix = sh.sel[0]; rank = (int)sh.sel[1]; }
         else prefix = (prefix << 8) | sh.sel[0];
-        __syncthreads();
+        stats_sync<NT>();
     }
     return prefix;
 }
@@ -327,23 +357,31 @@ __device__ __forceinline__ int stats_last_below(double limit, double off, double
     return lo;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const StatsArgs a)
 {
-    extern __shared__ __align__(16) int16_t smem_stage[];
-    __shared__ StatsShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int GROUPS = SQK_STATS_THREADS / NT;
+    constexpr int WARPS = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x % NT, gi = threadIdx.x / NT, lane = tid & 31, warp = tid >> 5;
+    const size_t group_bytes = ((sizeof(StatsShared) + 15) & ~(size_t)15) + (size_t)a.cap * sizeof(int16_t);
+    unsigned char *mine = smem_raw + gi * group_bytes;
+    StatsShared &sh = *reinterpret_cast<StatsShared *>(mine);
+    int16_t *smem_stage = reinterpret_cast<int16_t *>(mine + ((sizeof(StatsShared) + 15) & ~(size_t)15));
     int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
     resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
     const bool pa_mode = (a.mode == SQK_STATS_SEGMENTER && a.pa_offset != nullptr);
+    const int64_t slot = (int64_t)blockIdx.x * GROUPS + gi;
 
-    for (int64_t i = blockIdx.x; i < a.n_reads; i += gridDim.x) {
+    for (int64_t i = slot; i < a.n_reads; i += (int64_t)gridDim.x * GROUPS) {
         const int64_t r = a.read0 + i;
         const int64_t begin = a.offsets[r];
         int64_t len = a.offsets[r + 1] - begin;
         if (a.mode == SQK_STATS_SEGMENTER) len = sqk_truncate_len(len, a.num);
         const int64_t end = begin + len;
         const bool staged = (a.mode != SQK_STATS_NONE);
-        int16_t *stage = (len <= a.cap) ? smem_stage : a.gstage + (int64_t)blockIdx.x * a.gstage_stride;
+        const bool in_smem = (len <= a.cap);
+        int16_t *stage = in_smem ? smem_stage : a.gstage + slot * a.gstage_stride;
 
         // ---- outlier window on the raw sample (inclusive) ------------------------------------
         int out_lo = a.lo + 1, out_hi = a.hi - 1;
@@ -363,53 +401,71 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
         long long sum = 0;
         int total = 0;
         const int64_t blk0 = aligned_block_start(a.base, begin);
-        for (int64_t cb = blk0; cb < end; cb += SQK_STATS_THREADS * 8) {
-            const int64_t blk = cb + tid * 8;
-            Samples8 s;
-            unsigned keep = 0;
-            if (blk < end && blk + 8 > begin) {
-                s = load_block8(a.base, blk, alloc_lo, alloc_hi);
+        constexpr int U = 4;                      // 16-byte loads in flight per thread
+        for (int64_t cb = blk0; cb < end; cb += (int64_t)NT * 8 * U) {
+            Samples8 sv[U];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int v = s.get(e);
-                    const int64_t idx = blk + e;
-                    if (idx >= begin && idx < end && v >= out_lo && v <= out_hi) { keep |= 1u << e; sum += v; }
+            for (int u = 0; u < U; u++) {
+                const int64_t blk = cb + ((int64_t)u * NT + tid) * 8;
+                if (blk < end && blk + 8 > begin) sv[u] = load_block8(a.base, blk, alloc_lo, alloc_hi);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t blk = cb + ((int64_t)u * NT + tid) * 8;
+                if (cb + (int64_t)u * NT * 8 >= end) break;           // uniform over the group
+                const Samples8 s = sv[u];
+                unsigned keep = 0;
+                if (blk < end && blk + 8 > begin) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int v = s.get(e);
+                        const int64_t idx = blk + e;
+                        if (idx >= begin && idx < end && v >= out_lo && v <= out_hi) { keep |= 1u << e; sum += v; }
+                    }
                 }
-            }
-            const int cnt = __popc(keep);
-            int incl = cnt;
+                const int cnt = __popc(keep);
+                int incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane == 31) sh.warp_tot[warp] = incl;
-            __syncthreads();
-            int pos = total + incl - cnt, all = 0;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                int pos = total + incl - cnt, all;
+                if (NT == 32) {
+                    all = __shfl_sync(SQK_FULL_MASK, incl, 31);
+                } else {
+                    if (lane == 31) sh.warp_tot[warp] = incl;
+                    __syncthreads();
+                    all = 0;
 #pragma unroll
-            for (int w = 0; w < SQK_STATS_WARPS; w++) {
-                const int t = sh.warp_tot[w];
-                if (w < warp) pos += t;
-                all += t;
-            }
-            if (staged && keep) {
+                    for (int w = 0; w < WARPS; w++) {
+                        const int t = sh.warp_tot[w];
+                        if (w < warp) pos += t;
+                        all += t;
+                    }
+                }
+                if (staged && keep) {
 #pragma unroll
-                for (int e = 0; e < 8; e++)
-                    if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+                    for (int e = 0; e < 8; e++)
+                        if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+                }
+                total += all;
+                if (NT > 32) __syncthreads();
             }
-            total += all;
-            __syncthreads();
         }
         const int n = total;
 
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SQK_FULL_MASK, sum, d);
-        if (lane == 0) sh.sum_part[warp] = (unsigned long long)sum;
-        __syncthreads();
-        long long tot_sum = 0;
+        long long tot_sum = sum;
+        if (NT > 32) {
+            if (lane == 0) sh.sum_part[warp] = (unsigned long long)sum;
+            __syncthreads();
+            tot_sum = 0;
 #pragma unroll
-        for (int w = 0; w < SQK_STATS_WARPS; w++) tot_sum += (long long)sh.sum_part[w];
-        __syncthreads();   // staged samples visible to all; sum_part reusable
+            for (int w = 0; w < WARPS; w++) tot_sum += (long long)sh.sum_part[w];
+        }
+        stats_sync<NT>();   // staged samples visible to the whole group
 
         ReadStats out;
         out.center = 0.0; out.scale = 1.0; out.n_kept = n; out.flags = 0; out.seg_lo = 0; out.seg_hi = -1;
@@ -421,16 +477,16 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 // integer samples: the sum is exact in any order
                 const double mean = __ddiv_rn((double)tot_sum, (double)n);
                 auto sq = [stage, mean](int q) -> double { const double d = __dsub_rn((double)stage[q], mean); return __dmul_rn(d, d); };
-                sd = __dsqrt_rn(__ddiv_rn(stats_sum(sq, n, sh), (double)n));
+                sd = __dsqrt_rn(__ddiv_rn(stats_sum<NT>(sq, n, sh), (double)n));
             } else {
                 // pA samples are not integers: np.std's mean is itself a pairwise sum
                 auto val = [stage, pa_off, pa_unit](int q) -> double { return sqk_pa_value((int)stage[q], pa_off, pa_unit); };
-                const double mean = __ddiv_rn(stats_sum(val, n, sh), (double)n);
+                const double mean = __ddiv_rn(stats_sum<NT>(val, n, sh), (double)n);
                 auto sq = [stage, pa_off, pa_unit, mean](int q) -> double {
                     const double d = __dsub_rn(sqk_pa_value((int)stage[q], pa_off, pa_unit), mean);
                     return __dmul_rn(d, d);
                 };
-                sd = __dsqrt_rn(__ddiv_rn(stats_sum(sq, n, sh), (double)n));
+                sd = __dsqrt_rn(__ddiv_rn(stats_sum<NT>(sq, n, sh), (double)n));
             }
             if (a.mode == SQK_STATS_ZSCALE) {
                 if (sd == 0.0) sd = 1.0;          // sklearn _handle_zeros_in_scale
@@ -443,14 +499,14 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
             auto key_x = [stage](int q) -> uint32_t { return (uint32_t)((int)stage[q] + 32768); };
             int lo_v, hi_v;   // the two middle order statistics (equal for odd n)
             if (direct) {
-                stats_histogram(stage, n, out_lo, nbins, sh);
+                stats_histogram<NT>(stage, n, out_lo, sh);
                 lo_v = out_lo + stats_hist_select(sh, nbins, (n - 1) / 2);
                 hi_v = (n & 1) ? lo_v : out_lo + stats_hist_select(sh, nbins, n / 2);
             } else if (n & 1) {
-                lo_v = hi_v = (int)stats_select(key_x, n, (n - 1) / 2, sh) - 32768;
+                lo_v = hi_v = (int)stats_select<NT>(key_x, n, (n - 1) / 2, sh) - 32768;
             } else {
-                lo_v = (int)stats_select(key_x, n, n / 2 - 1, sh) - 32768;
-                hi_v = (int)stats_select(key_x, n, n / 2, sh) - 32768;
+                lo_v = (int)stats_select<NT>(key_x, n, n / 2 - 1, sh) - 32768;
+                hi_v = (int)stats_select<NT>(key_x, n, n / 2, sh) - 32768;
             }
             const int med2 = lo_v + hi_v;   // 2 * median of the raw integers
             if (a.mode == SQK_STATS_MEDMAD) {
@@ -465,10 +521,10 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                     const int d1 = (n & 1) ? d0 : stats_hist_mad(sh, out_lo, nbins, med2, n / 2);
                     mad = (double)(d0 + d1) * 0.25;
                 } else if (n & 1) {
-                    mad = (double)stats_select(key_d, n, (n - 1) / 2, sh) * 0.5;
+                    mad = (double)stats_select<NT>(key_d, n, (n - 1) / 2, sh) * 0.5;
                 } else {
-                    const uint32_t d0 = stats_select(key_d, n, n / 2 - 1, sh);
-                    const uint32_t d1 = stats_select(key_d, n, n / 2, sh);
+                    const uint32_t d0 = stats_select<NT>(key_d, n, n / 2 - 1, sh);
+                    const uint32_t d1 = stats_select<NT>(key_d, n, n / 2, sh);
                     mad = (double)(d0 + d1) * 0.25;
                 }
                 const double scaled = __dmul_rn(mad, 1.4826);
@@ -496,10 +552,11 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 out.center = top; out.scale = bot;
             }
         }
+
         if (tid == 0) {
             a.stats[i] = out;
             if (a.n_kept_out) a.n_kept_out[i] = n;
         }
-        __syncthreads();
+        stats_sync<NT>();
     }
 }
