@@ -165,7 +165,10 @@ typedef struct {
 SQK_API int sqk_ctx_enable_timing(sqk_ctx *ctx, int on);
 SQK_API int sqk_ctx_get_timing(sqk_ctx *ctx, sqk_timing *out, int reset);
 
-/* Tuning knob for experiments: force lanes-per-read of the DTW kernel (0 = automatic). */
+/* Tuning knobs.  dtw_lanes: force lanes-per-read of the DTW kernel (0 = automatic).  chunk_samples: host mode,
+ * samples per in-flight chunk of the H2D | compute | D2H pipeline (0 = default 64 Mi; the first two chunks
+ * are 1/4 and 1/2 of it). */
+SQK_API int sqk_ctx_set_chunk_samples(sqk_ctx *ctx, int64_t samples);
 SQK_API int sqk_ctx_set_dtw_lanes(sqk_ctx *ctx, int lanes);
 
 #ifdef __cplusplus

@@ -46,7 +46,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sqk_version", "sqk_last_error", "sqk_ctx_create", "sqk_ctx_destroy", "sqk_ctx_set_stream", "sqk_ctx_sync",
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
-    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes",
+    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples",
 ]
 
 _lib = None
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.sqk_ctx_enable_timing.argtypes = [vp, C.c_int]
     L.sqk_ctx_get_timing.argtypes = [vp, C.POINTER(Timing), C.c_int]
     L.sqk_ctx_set_dtw_lanes.argtypes = [vp, C.c_int]
+    L.sqk_ctx_set_chunk_samples.argtypes = [vp, i64]
     for name in EXPORTS:
         if name not in ("sqk_version", "sqk_last_error"):
             getattr(L, name).restype = C.c_int

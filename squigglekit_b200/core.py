@@ -112,6 +112,10 @@ class Context:
     def set_dtw_lanes(self, lanes: int):
         _cabi.check(self._lib.sqk_ctx_set_dtw_lanes(self._h, int(lanes)))
 
+    def set_chunk_samples(self, samples: int):
+        """Host mode: samples per in-flight chunk of the copy/compute pipeline (0 = default)."""
+        _cabi.check(self._lib.sqk_ctx_set_chunk_samples(self._h, int(samples)))
+
     def sync(self):
         _cabi.check(self._lib.sqk_ctx_sync(self._h))
 

@@ -148,6 +148,7 @@ struct sqk_ctx {
     std::vector<cudaEvent_t> pool;
     sqk_timing acc{};
     int force_lanes = 0;
+    int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1;
 };
 
@@ -643,6 +644,14 @@ int sqk_ctx_get_timing(sqk_ctx *c, sqk_timing *out, int reset)
     return SQK_OK;
 }
 
+int sqk_ctx_set_chunk_samples(sqk_ctx *c, int64_t samples)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (samples < 0) return fail(SQK_ERR_ARG, "samples < 0");
+    c->chunk_samples = samples;
+    return SQK_OK;
+}
+
 int sqk_ctx_set_dtw_lanes(sqk_ctx *c, int lanes)
 {
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
@@ -696,7 +705,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
     CU(cudaStreamSynchronize(c->slot[0].stream));
     std::vector<int64_t> cuts;
-    plan_chunks(offsets, n_reads, chunk_samples(), cuts);
+    plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
     const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
@@ -756,7 +765,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     }
     if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
     std::vector<int64_t> cuts;
-    plan_chunks(offsets, n_reads, chunk_samples(), cuts);
+    plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
     const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];

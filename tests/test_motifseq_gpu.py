@@ -287,3 +287,34 @@ def test_argument_errors_are_reported_not_crashed(ctx):
     want, _ = oracle_hits(sig, off, motif, "zscale")
     hits, _ = ctx.motifseq(sig, off, motif, scale="zscale")
     assert_hits_equal(hits[:, 0], want, what="after errors")
+
+
+@pytest.mark.parametrize("chunk", [4096, 50_000, 1 << 20])
+def test_host_pipeline_chunking(ctx, chunk):
+    """Host mode splits the batch into chunks (two slots, copies overlapped with kernels, results through
+    pinned staging).  Tiny chunks force many of them, with ragged reads straddling every kind of boundary,
+    a read longer than a chunk, empty reads, pageable and pinned buffers: results must not depend on it."""
+    motif = synth.make_motif()
+    rng = np.random.default_rng(chunk)
+    lengths = [int(v) for v in rng.integers(0, 9000, 120)] + [0, 0, 70_000, 1, 5000]
+    sig, off = synth.ragged_reads_np(lengths, motif)
+    want, kept_w = oracle_hits(sig, off, motif, "zscale")
+    ok = kept_w > 0
+    ctx.set_chunk_samples(chunk)
+    try:
+        hits, kept = ctx.motifseq(sig, off, [motif, motif[:33]], scale="zscale")
+        p_sig = sqk.pinned_empty(sig.size, np.int16); p_sig[:] = sig
+        p_hits = sqk.pinned_empty((len(lengths), 2), sqk.HIT_DTYPE)
+        hits2, kept2 = ctx.motifseq(p_sig, off, [motif, motif[:33]], scale="zscale", out=p_hits)
+        segs, nsegs = ctx.segmenter(sig, off, sqk.SegConfig(max_segs=64))
+    finally:
+        ctx.set_chunk_samples(0)
+    assert_hits_equal(hits[ok, 0], want[ok], kept, kept_w, f"chunk={chunk}")
+    assert np.array_equal(hits.view(np.uint8), np.asarray(hits2).view(np.uint8)) and np.array_equal(kept, kept2)
+    want2, _ = oracle_hits(sig, off, motif[:33], "zscale")
+    assert_hits_equal(hits[ok, 1], want2[ok], what=f"chunk={chunk} model 2")
+    want_s, want_n = oracle.segmenter_batch(sig, off, oracle.SegCfg(), 0, 900, 0, 64)
+    assert np.array_equal(nsegs, want_n)
+    for r in range(nsegs.size):
+        assert np.array_equal(segs[r, :nsegs[r]], want_s[r, :want_n[r]])
+    sqk.pinned_free(p_sig); sqk.pinned_free(p_hits)
