@@ -102,17 +102,20 @@ def iter_reads(args):
             yield from _fast5_reads(args, fast5_file, fast5_file)
     elif args.signal:
         with _opener(args.signal)(args.signal, 'rt') as s:
-            for l in s:
-                l = l.strip('\n').split('\t')
-                fast5 = l[0]
-                if len(l) <= args.start_col:
+            from .cli_motifseq import split_signal_columns
+            for line in s:
+                line = line.rstrip('\n')
+                head, tail = split_signal_columns(line, args.start_col)
+                fast5 = head[0]
+                if tail is None:
                     sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
                     continue
-                if "." in l[args.start_col]:
+                first = tail.split('\t', 1)[0]
+                if "." in first:                      # the reference switches to float parsing on this test (:198)
                     sys.stderr.write("{}: float (pA) signal is not supported by the GPU path; extract raw signal with "
                                      "SquigglePull -r\n".format(fast5))
                     continue
-                sig = np.array([int(i) for i in l[args.start_col:]], dtype=np.int64)
+                sig = np.fromstring(tail, dtype=np.int64, sep='\t')
                 if not sig.any():
                     sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
                     continue

@@ -1,0 +1,66 @@
+"""Two-rank GPU test (NCCL): contiguous read shards per rank + one all-gather of the hit records must equal the
+single-GPU result byte for byte.  Skipped when fewer than two GPUs are visible (the driver's -m gpu run uses
+one)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["SQK_ROOT"])
+    import squigglekit_b200 as sqk
+    from squigglekit_b200 import synth
+    from squigglekit_b200.dist import allgather_records, env_rank_world, shard_bounds
+
+    rank, world, local = env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    motif = synth.make_motif()
+    n_reads = 1001                                   # uneven shards
+    sig, off, _ = synth.motifseq_reads_np(n_reads, 2048, motif)
+    lo, hi = shard_bounds(n_reads, rank, world)
+    counts = [shard_bounds(n_reads, r, world)[1] - shard_bounds(n_reads, r, world)[0] for r in range(world)]
+    ctx = sqk.Context(local)
+    dsig = torch.from_numpy(sig).cuda()
+    doff = torch.from_numpy(off[lo:hi + 1].copy()).cuda()        # absolute offsets of this rank's block
+    hits, _ = ctx.motifseq(dsig, doff, motif, scale="zscale", max_read_len=2048)
+    full = allgather_records(hits, counts)
+    torch.cuda.synchronize()
+    if rank == 0:
+        one, _ = ctx.motifseq(dsig, torch.from_numpy(off).cuda(), motif, scale="zscale", max_read_len=2048)
+        torch.cuda.synchronize()
+        assert full.shape == one.shape and torch.equal(full, one), "sharded result differs from single-GPU result"
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_two_rank_shards_equal_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), SQK_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out[-3000:]
+        assert f"rank {rank} ok" in out
