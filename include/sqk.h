@@ -95,7 +95,8 @@ typedef struct {
 } sqk_motif_params;
 
 typedef struct {
-    int32_t start; /* path[1][0];  -1: read empty after outlier removal; -2: scale undefined (MAD == 0) */
+    int32_t start; /* path[1][0];  -1: read empty after outlier removal; -2: scale undefined (MAD == 0);
+                      -3: read longer than the max_read_len the caller declared (not processed) */
     int32_t end;   /* path[1][-1] == np.argmin(cost[-1, :]) */
     double dist;   /* cost[-1, end]; NaN when start < 0 */
 } sqk_hit;
@@ -140,7 +141,8 @@ typedef struct {
 } sqk_seg_params;
 
 /* segs: [n_reads][max_segs][2] int32 (start, end); n_segs[n_reads]: segments found (0 == the
- * reference's `False`); a count above max_segs means the row was truncated to max_segs. */
+ * reference's `False`); a count above max_segs means the row was truncated to max_segs; -1 = read longer than the
+ * declared max_read_len (not processed). */
 SQK_API int sqk_segmenter(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
                   int64_t max_read_len, const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
 

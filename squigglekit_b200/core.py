@@ -261,6 +261,8 @@ def segs_to_lists(segs: np.ndarray, n_segs: np.ndarray):
     cap = segs.shape[1]
     for r in range(n_segs.shape[0]):
         n = int(n_segs[r])
+        if n < 0:
+            raise ValueError(f"read {r} is longer than the max_read_len passed to segmenter()")
         if n > cap:
             raise OverflowError(f"read {r}: {n} segments > max_segs={cap}")
         out.append([[int(segs[r, i, 0]), int(segs[r, i, 1])] for i in range(n)] if n else False)

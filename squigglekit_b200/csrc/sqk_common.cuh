@@ -24,6 +24,7 @@ struct __align__(8) ReadStats {
 static_assert(sizeof(ReadStats) == 40, "ReadStats layout");
 
 #define SQK_FLAG_DEGENERATE 1
+#define SQK_FLAG_TOO_LONG 2     // read longer than the max_read_len the caller declared: not processed
 
 // convert_to_pA_numpy + np.round(.., 2)  (segmenter.py:515-517, 345-349): every op rounds once, as numpy's
 //   (d + offset) * raw_unit ; multiply by 100 ; rint ; divide by 100.

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs 
     const int64_t begin = a.offsets[r];
     const int64_t end = begin + sqk_truncate_len(a.offsets[r + 1] - begin, a.num);
     const ReadStats st = a.stats[i];
+    if (st.flags & SQK_FLAG_TOO_LONG) { a.n_segs[i] = -1; return; }   // longer than the declared max_read_len
     const int seg_lo = st.seg_lo, seg_hi = st.seg_hi, out_lo = st.out_lo, out_hi = st.out_hi;
     int32_t *out = a.segs + (int64_t)i * a.max_segs * 2;
 

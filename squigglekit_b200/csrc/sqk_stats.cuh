@@ -381,6 +381,17 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
         const int64_t end = begin + len;
         const bool staged = (a.mode != SQK_STATS_NONE);
         const bool in_smem = (len <= a.cap);
+        if (staged && !in_smem && (a.gstage == nullptr || len > a.gstage_stride)) {
+            // longer than the max_read_len the caller declared: no staging row was provisioned for it
+            if (tid == 0) {
+                ReadStats bad;
+                bad.center = 0.0; bad.scale = 1.0; bad.n_kept = 0; bad.flags = SQK_FLAG_TOO_LONG;
+                bad.seg_lo = 0; bad.seg_hi = -1; bad.out_lo = 1; bad.out_hi = 0;
+                a.stats[i] = bad;
+                if (a.n_kept_out) a.n_kept_out[i] = -1;
+            }
+            continue;
+        }
         int16_t *stage = in_smem ? smem_stage : a.gstage + slot * a.gstage_stride;
 
         // ---- outlier window on the raw sample (inclusive) ------------------------------------

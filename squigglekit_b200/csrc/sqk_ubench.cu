@@ -11,7 +11,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "sqk_dtw.cuh"
+#include "sqk_dtw_experiments.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 

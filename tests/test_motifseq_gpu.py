@@ -318,3 +318,23 @@ def test_host_pipeline_chunking(ctx, chunk):
     for r in range(nsegs.size):
         assert np.array_equal(segs[r, :nsegs[r]], want_s[r, :want_n[r]])
     sqk.pinned_free(p_sig); sqk.pinned_free(p_hits)
+
+
+def test_understated_max_read_len_is_flagged_not_overrun(ctx):
+    """Device mode trusts the caller's max_read_len for sizing the staging window; a longer read must come back
+    flagged (-3 / n_segs -1), never overrun shared memory."""
+    import torch
+    motif = synth.make_motif()
+    sig, off = synth.ragged_reads_np([1000, 200_000, 3000], motif)
+    want, kept_w = oracle_hits(sig, off, motif, "zscale")
+    hits_t, kept_t = ctx.motifseq(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), motif, scale="zscale",
+                                  max_read_len=3000)
+    torch.cuda.synchronize()
+    h = sqk.hits_from_torch(hits_t)[:, 0]
+    assert int(h["start"][1]) == -3 and int(kept_t[1]) == -1
+    assert_hits_equal(h[[0, 2]], want[[0, 2]], what="neighbours of the flagged read")
+    segs, nsegs = ctx.segmenter(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), sqk.SegConfig(), max_read_len=3000)
+    torch.cuda.synchronize()
+    assert int(nsegs[1]) == -1
+    with pytest.raises(ValueError):
+        sqk.segs_to_lists(segs.cpu().numpy(), nsegs.cpu().numpy())
