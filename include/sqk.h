@@ -156,6 +156,19 @@ SQK_API int sqk_segmenter_pa(sqk_ctx *ctx, const int16_t *signals, const int64_t
                              const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
 
 /* ---------------------------------------------------------------------------------------
+ * float64 signals.  The reference's `-s` path hands both tools whatever the TSV holds (MotifSeq.py:270
+ * `float(i) for i in l[8:]`; segmenter.py:198-199), e.g. SquigglePull's pA output.  Same semantics and outputs as
+ * sqk_motifseq / sqk_segmenter with `signals` as float64: outlier window, numpy-exact float statistics (pairwise
+ * mean / sigma, exact medians), then the same DTW / state-machine kernels.  Device mode needs one small
+ * synchronising copy (to size its scratch).  This path costs 18 bytes of HBM traffic per sample instead of 2.
+ * ------------------------------------------------------------------------------------- */
+SQK_API int sqk_motifseq_f64(sqk_ctx *ctx, const double *signals, const int64_t *offsets, int64_t n_reads,
+                             const double *models, const int32_t *model_offsets, int32_t n_models,
+                             const sqk_motif_params *params, int mem, sqk_hit *hits, int32_t *n_kept);
+SQK_API int sqk_segmenter_f64(sqk_ctx *ctx, const double *signals, const int64_t *offsets, int64_t n_reads,
+                              const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
+
+/* ---------------------------------------------------------------------------------------
  * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the
  * launching stream around each launch.  Off by default.  Reading the counters synchronises.
  * ------------------------------------------------------------------------------------- */

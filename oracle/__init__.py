@@ -19,9 +19,11 @@ from .cpu import (  # noqa: F401
     max_threads,
     medmad,
     motifseq_batch,
+    motifseq_batch_f64,
     np_median,
     np_sum,
     segmenter_batch,
     segmenter_batch_pa,
+    segmenter_batch_f64,
     zscale,
 )

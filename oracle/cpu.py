@@ -77,6 +77,10 @@ def lib() -> C.CDLL:
         L.orc_convert_to_pa.restype = None
         L.orc_segmenter_batch_pa.argtypes = [C.c_void_p, lp, C.c_int64, dp, dp, C.POINTER(_SegCfg), C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, ip, ip]
+        L.orc_motifseq_batch_f64.argtypes = [dp, lp, C.c_int64, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, ip]
+        L.orc_segmenter_batch_f64.argtypes = [dp, lp, C.c_int64, C.POINTER(_SegCfg), C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, ip, ip]
         _lib = L
     return _lib
 
@@ -225,4 +229,33 @@ def segmenter_batch_pa(signals, offsets, pa_offset, pa_scale, cfg: SegCfg = SegC
                                       lim_lo, lim_hi, num, max_segs, n_threads, _ip(segs), _ip(nsegs))
     if rc:
         raise RuntimeError("orc_segmenter_batch_pa failed")
+    return segs, nsegs
+
+
+def motifseq_batch_f64(signals, offsets, model, lo=0, hi=1200, scale="zscale", full_matrix=False, n_threads=0):
+    """float64 signals (the reference's `-s` path on a TSV of floats): scale_outliers -> normalise -> DTW."""
+    signals = np.ascontiguousarray(signals, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    model = np.ascontiguousarray(model, dtype=np.float64)
+    n = offsets.size - 1
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    kept = np.zeros(n, dtype=np.int32)
+    rc = lib().orc_motifseq_batch_f64(_dp(signals), _lp(offsets), n, _dp(model), model.size, lo, hi, SCALE_MODES[scale],
+                                      int(full_matrix), n_threads, hits.ctypes.data, _ip(kept))
+    if rc:
+        raise RuntimeError("orc_motifseq_batch_f64 failed")
+    return hits, kept
+
+
+def segmenter_batch_f64(signals, offsets, cfg: SegCfg = SegCfg(), lim_lo=0, lim_hi=900, num=0, max_segs=16, n_threads=0):
+    signals = np.ascontiguousarray(signals, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    segs = np.zeros((n, max_segs, 2), dtype=np.int32)
+    nsegs = np.zeros(n, dtype=np.int32)
+    c = cfg.c()
+    rc = lib().orc_segmenter_batch_f64(_dp(signals), _lp(offsets), n, C.byref(c), lim_lo, lim_hi, num, max_segs, n_threads,
+                                       _ip(segs), _ip(nsegs))
+    if rc:
+        raise RuntimeError("orc_segmenter_batch_f64 failed")
     return segs, nsegs

@@ -491,6 +491,81 @@ ORC_API int orc_segmenter_batch_pa(const int16_t *signals, const int64_t *offset
     return failed ? -1 : 0;
 }
 
+/* float64-signal variants of the two batch drivers: what the reference's `-s` path does with a TSV of floats
+ * (MotifSeq.py:270-298; segmenter.py:198-211). */
+ORC_API int orc_motifseq_batch_f64(const double *signals, const int64_t *offsets, int64_t n_reads,
+                                   const double *model, int n_model, int lo, int hi, int scale_mode,
+                                   int full_matrix, int n_threads, orc_hit *hits, int32_t *n_kept)
+{
+    int failed = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        orc_hit h; h.start = -1; h.end = -1; h.dist = NAN;
+        int64_t kept = 0;
+        if (len > 0) {
+            double *y = (double *)malloc((size_t)len * sizeof(double));
+            if (!y) failed = 1;
+            else {
+                for (int64_t i = 0; i < len; i++) {
+                    const double v = signals[offsets[r] + i];
+                    if (v > lo && v < hi) y[kept++] = v;
+                }
+                if (kept > 0) {
+                    if (scale_mode == 0) orc_zscale(y, kept, NULL, NULL);
+                    else if (scale_mode == 1) orc_medmad(y, kept, NULL, NULL);
+                    int rc = full_matrix
+                        ? orc_dtw_subsequence(model, n_model, y, (int)kept, NULL, &h, NULL, NULL, NULL)
+                        : orc_dtw_subsequence_rolling(model, n_model, y, (int)kept, &h, NULL);
+                    if (rc) failed = 1;
+                }
+                free(y);
+            }
+        }
+        hits[r] = h;
+        if (n_kept) n_kept[r] = (int32_t)kept;
+    }
+    return failed ? -1 : 0;
+}
+
+ORC_API int orc_segmenter_batch_f64(const double *signals, const int64_t *offsets, int64_t n_reads,
+                                    const orc_seg_cfg *cfg, int lim_lo, int lim_hi, int num,
+                                    int max_segs, int n_threads, int32_t *segs, int32_t *n_segs)
+{
+    int failed = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t r = 0; r < n_reads; r++) {
+        int64_t len = offsets[r + 1] - offsets[r];
+        int64_t use;
+        if (num == 0) use = len - 1;
+        else if (num > 0) use = num < len ? num : len;
+        else use = len + num;
+        if (use < 0) use = 0;
+        int cnt = 0;
+        if (use > 0) {
+            double *y = (double *)malloc((size_t)use * sizeof(double));
+            if (!y) failed = 1;
+            else {
+                int64_t kept = 0;
+                for (int64_t i = 0; i < use; i++) {
+                    const double v = signals[offsets[r] + i];
+                    if (v > lim_lo && v < lim_hi) y[kept++] = v;
+                }
+                if (kept > 0) cnt = orc_get_segs(y, kept, cfg, segs + (size_t)r * max_segs * 2, max_segs, NULL);
+                free(y);
+            }
+        }
+        n_segs[r] = cnt;
+    }
+    return failed ? -1 : 0;
+}
+
 ORC_API int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -46,7 +46,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sqk_version", "sqk_last_error", "sqk_ctx_create", "sqk_ctx_destroy", "sqk_ctx_set_stream", "sqk_ctx_sync",
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
-    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples",
+    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.sqk_motifseq_trace.argtypes = [vp, vp, i64, vp, i32, C.POINTER(MotifParams), vp, vp, i64, C.POINTER(i64), vp]
     L.sqk_segmenter.argtypes = [vp, vp, vp, i64, i64, C.POINTER(SegParams), C.c_int, vp, vp]
     L.sqk_segmenter_pa.argtypes = [vp, vp, vp, i64, i64, vp, vp, C.POINTER(SegParams), C.c_int, vp, vp]
+    L.sqk_motifseq_f64.argtypes = [vp, vp, vp, i64, vp, vp, i32, C.POINTER(MotifParams), C.c_int, vp, vp]
+    L.sqk_segmenter_f64.argtypes = [vp, vp, vp, i64, C.POINTER(SegParams), C.c_int, vp, vp]
     L.sqk_ctx_enable_timing.argtypes = [vp, C.c_int]
     L.sqk_ctx_get_timing.argtypes = [vp, C.POINTER(Timing), C.c_int]
     L.sqk_ctx_set_dtw_lanes.argtypes = [vp, C.c_int]

@@ -8,6 +8,8 @@ Deliberate differences, all loud:
     never searches) as well as the bait format.
   * ``-i`` (scrappie simulation of a fasta) needs the scrappie neural network: not available -> error.
   * ``-v`` / ``--save`` plotting is out of scope -> warning, rows are still printed.
+  * ``-s`` files with float (pA) columns run through the float64 front end (same results as the reference's
+    float path); ``-x`` is only available for raw integer signal.
   * reads that are empty after outlier removal, or whose MAD is 0 under medmad, are reported on stderr
     and skipped (the reference raises / prints NaN rows for them).
 """
@@ -114,11 +116,11 @@ def iter_reads(args):
                     sys.stderr.write("No Signal found - please check signal format\n")
                     continue
                 ints = np.rint(vals)
-                if not np.array_equal(ints, vals) or ints.min() < -32768 or ints.max() > 32767:
-                    sys.stderr.write("{}: non-integer (pA) signal is not supported by the GPU path; extract raw "
-                                     "signal with SquigglePull -r\n".format(head[0]))
-                    continue
-                yield head[0], head[1] if len(head) > 1 else "", ints.astype(np.int16)
+                if np.array_equal(ints, vals) and ints.min() >= -32768 and ints.max() <= 32767:
+                    sig = ints.astype(np.int16)          # raw DAC values: the int16 kernels (2 bytes/sample)
+                else:
+                    sig = vals                           # pA or any other float signal: the float64 front end
+                yield head[0], head[1] if len(head) > 1 else "", sig
 
 
 def split_signal_columns(line, start_col):
@@ -156,6 +158,8 @@ def flush(ctx, args, batch, model, m_order, L, out):
     sigs = [b[2] for b in batch]
     offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
     np.cumsum([s.size for s in sigs], out=offsets[1:])
+    if any(x.dtype.kind == "f" for x in sigs):
+        sigs = [x.astype(np.float64) for x in sigs]      # a batch with float reads goes through the float64 path as a whole
     signals = np.concatenate(sigs) if sigs else np.zeros(0, dtype=np.int16)
     hits, kept = ctx.motifseq(signals, offsets, [model[n] for n in m_order], scale=args.scale,
                               scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision)
@@ -168,7 +172,9 @@ def flush(ctx, args, batch, model, m_order, L, out):
                 sys.stderr.write("{} {}: {} - skipped\n".format(fast5, read_id, why))
                 continue
             extract = None
-            if args.sig_extract:
+            if args.sig_extract and sig.dtype.kind == "f":
+                sys.stderr.write("{} {}: -x is not available for float (pA) signal input - row printed without the signal\n".format(fast5, read_id))
+            elif args.sig_extract:
                 _, norm, _ = ctx.motifseq_trace(sig, model[name], scale=args.scale, scale_low=args.scale_low,
                                                 scale_hi=args.scale_hi, precision=args.precision)
                 extract = norm[start:end]

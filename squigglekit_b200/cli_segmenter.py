@@ -8,9 +8,10 @@ fast5 input follows the reference: by default each read is converted to pA round
 segmentation (:344-349, :366-370) -- done on the GPU from the raw samples and the per-read calibration --
 and ``--raw_signal`` segments the raw integers.
 
+``-s`` files may hold raw integers (int16 kernels) or floats such as SquigglePull's pA output (float64 front
+end, same results as the reference's float branch).
+
 Deliberate differences, all loud:
-  * ``-s`` files with float (pA) columns are rejected per read: arbitrary float signal has no int16 form
-    (listed as "next" in DESIGN.md); raw integer columns work.
   * ``-v`` plotting is out of scope -> warning.
 """
 from __future__ import annotations
@@ -112,15 +113,18 @@ def iter_reads(args):
                     continue
                 first = tail.split('\t', 1)[0]
                 if "." in first:                      # the reference switches to float parsing on this test (:198)
-                    sys.stderr.write("{}: float (pA) signal is not supported by the GPU path; extract raw signal with "
-                                     "SquigglePull -r\n".format(fast5))
+                    sig = np.fromstring(tail, dtype=np.float64, sep='\t')
+                    if not sig.any():
+                        sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
+                        continue
+                    yield fast5, sig, 0.0, 1.0        # float64 front end
                     continue
                 sig = np.fromstring(tail, dtype=np.int64, sep='\t')
                 if not sig.any():
                     sys.stderr.write("No signal found in file: {} {}".format(args.signal, fast5))
                     continue
                 if sig.min() < -32768 or sig.max() > 32767:
-                    sys.stderr.write("{}: samples outside the int16 range\n".format(fast5))
+                    yield fast5, sig.astype(np.float64), 0.0, 1.0
                     continue
                 yield fast5, sig.astype(np.int16), 0.0, 1.0
 
@@ -132,6 +136,8 @@ def flush(ctx, args, cfg, batch, out):
     sigs = [b[1] for b in batch]
     offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
     np.cumsum([s.size for s in sigs], out=offsets[1:])
+    if any(x.dtype.kind == "f" for x in sigs):
+        sigs = [x.astype(np.float64) for x in sigs]
     if args.signal or args.raw_signal:
         segs, nsegs = ctx.segmenter(np.concatenate(sigs), offsets, cfg)
     else:

@@ -150,8 +150,8 @@ class Context:
         n_models = moffs.size - 1
         if _is_torch(signals):
             import torch
-            if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
-                raise TypeError("device mode needs int16 signals and int64 offsets")
+            if signals.dtype not in (torch.int16, torch.float64) or offsets.dtype != torch.int64:
+                raise TypeError("device mode needs int16 (or float64) signals and int64 offsets")
             if not (signals.is_cuda and offsets.is_cuda and signals.is_contiguous() and offsets.is_contiguous()):
                 raise ValueError("device mode needs contiguous CUDA tensors")
             n_reads = offsets.numel() - 1
@@ -159,16 +159,29 @@ class Context:
             hits = out if out is not None else torch.empty((n_reads, n_models, 16), dtype=torch.uint8, device=dev)
             kept = torch.empty(n_reads, dtype=torch.int32, device=dev) if want_kept else None
             self._use_torch_stream()
+            if signals.dtype == torch.float64:
+                _cabi.check(self._lib.sqk_motifseq_f64(
+                    self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, mvec.ctypes.data, moffs.ctypes.data, n_models,
+                    C.byref(params), _cabi.SQK_MEM_DEVICE, hits.data_ptr(), kept.data_ptr() if kept is not None else None))
+                return hits, kept
             _cabi.check(self._lib.sqk_motifseq(
                 self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, int(max_read_len), mvec.ctypes.data,
                 moffs.ctypes.data, n_models, C.byref(params), _cabi.SQK_MEM_DEVICE, hits.data_ptr(),
                 kept.data_ptr() if kept is not None else None))
             return hits, kept
-        signals = np.ascontiguousarray(signals, dtype=np.int16)
+        signals = np.asarray(signals)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n_reads = offsets.size - 1
         hits = out if out is not None else np.zeros((n_reads, n_models), dtype=HIT_DTYPE)
         kept = np.zeros(n_reads, dtype=np.int32) if want_kept else None
+        if signals.dtype.kind == "f":
+            # float signal (e.g. pA values from a SquigglePull TSV): the float64 front end, same outputs
+            signals = np.ascontiguousarray(signals, dtype=np.float64)
+            _cabi.check(self._lib.sqk_motifseq_f64(
+                self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, mvec.ctypes.data, moffs.ctypes.data, n_models,
+                C.byref(params), _cabi.SQK_MEM_HOST, hits.ctypes.data, kept.ctypes.data if kept is not None else None))
+            return hits, kept
+        signals = np.ascontiguousarray(signals, dtype=np.int16)
         _cabi.check(self._lib.sqk_motifseq(
             self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len), mvec.ctypes.data,
             moffs.ctypes.data, n_models, C.byref(params), _cabi.SQK_MEM_HOST, hits.ctypes.data,
@@ -211,13 +224,19 @@ class Context:
         use_pa = pa_offset is not None
         if _is_torch(signals):
             import torch
-            if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
-                raise TypeError("device mode needs int16 signals and int64 offsets")
+            if signals.dtype not in (torch.int16, torch.float64) or offsets.dtype != torch.int64:
+                raise TypeError("device mode needs int16 (or float64) signals and int64 offsets")
             n_reads = offsets.numel() - 1
             dev = signals.device
             segs = torch.zeros((n_reads, cfg.max_segs, 2), dtype=torch.int32, device=dev)
             nsegs = torch.zeros(n_reads, dtype=torch.int32, device=dev)
             self._use_torch_stream()
+            if signals.dtype == torch.float64:
+                if use_pa:
+                    raise ValueError("pa_offset/pa_scale apply to raw int16 signals, not to float signals")
+                _cabi.check(self._lib.sqk_segmenter_f64(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, C.byref(p),
+                                                        _cabi.SQK_MEM_DEVICE, segs.data_ptr(), nsegs.data_ptr()))
+                return segs, nsegs
             if use_pa:
                 po = torch.as_tensor(pa_offset, dtype=torch.float64, device=dev).contiguous()
                 ps = torch.as_tensor(pa_scale, dtype=torch.float64, device=dev).contiguous()
@@ -230,11 +249,19 @@ class Context:
                                                     int(max_read_len), C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(),
                                                     nsegs.data_ptr()))
             return segs, nsegs
-        signals = np.ascontiguousarray(signals, dtype=np.int16)
+        signals = np.asarray(signals)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n_reads = offsets.size - 1
         segs = np.zeros((n_reads, cfg.max_segs, 2), dtype=np.int32)
         nsegs = np.zeros(n_reads, dtype=np.int32)
+        if signals.dtype.kind == "f":
+            if use_pa:
+                raise ValueError("pa_offset/pa_scale apply to raw int16 signals, not to float signals")
+            signals = np.ascontiguousarray(signals, dtype=np.float64)
+            _cabi.check(self._lib.sqk_segmenter_f64(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, C.byref(p),
+                                                    _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
+            return segs, nsegs
+        signals = np.ascontiguousarray(signals, dtype=np.int16)
         if use_pa:
             po = np.ascontiguousarray(pa_offset, dtype=np.float64)
             ps = np.ascontiguousarray(pa_scale, dtype=np.float64)

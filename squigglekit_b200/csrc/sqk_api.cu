@@ -14,6 +14,7 @@
 
 #include "sqk_dtw_launch.cuh"
 #include "sqk_segmenter.cuh"
+#include "sqk_f64.cuh"
 #include "sqk_stats.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -94,7 +95,7 @@ struct Pending { void *dst; const void *src; size_t bytes; };
 
 struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
-    DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale;
+    DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -469,6 +470,103 @@ static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v
     return SQK_OK;
 }
 
+// ---- float64-signal front end (sqk_f64.cuh): one extra kernel, then K2 / K3 as usual -------------------
+struct View64 {
+    const double *base;       // base[i] = absolute sample i
+    const int64_t *offsets;   // indexable by absolute read id
+    int64_t read0, n_reads;
+    int64_t sample0, n_samples;   // the absolute sample range these reads cover
+};
+
+static int launch_f64_front(sqk_ctx *c, Slot &s, cudaStream_t st, const View64 &v, int mode, int lo, int hi, int num,
+                            double std_scale, int32_t *d_nkept)
+{
+    TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
+    TRY(ensure(s.ynorm, (size_t)std::max<int64_t>(v.n_samples, 1) * sizeof(double)));
+    if (mode == SQK_STATS_SEGMENTER) TRY(ensure(s.codes, (size_t)std::max<int64_t>(v.n_samples, 8) * sizeof(int16_t) + 32));
+    F64Args a{};
+    a.base = v.base; a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = v.n_reads;
+    a.stats = (ReadStats *)s.stats.p; a.n_kept_out = d_nkept;
+    a.mode = mode; a.lo = clamp_lim(lo); a.hi = clamp_lim(hi); a.num = num; a.std_scale = std_scale;
+    a.ynorm = (double *)s.ynorm.p - v.sample0;
+    a.codes = mode == SQK_STATS_SEGMENTER ? (int16_t *)s.codes.p - v.sample0 : nullptr;
+    const int dyn = (int)((sizeof(StatsShared) + 15) & ~(size_t)15);
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * 8));
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_STATS, st, &eb));
+    sqk_f64_front_kernel<<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+static int enqueue_motifseq_f64(sqk_ctx *c, Slot &s, cudaStream_t st, const View64 &v, const double *d_models,
+                                const int32_t *h_model_offsets, int n_models, const sqk_motif_params *p, sqk_hit *d_hits,
+                                int32_t *d_nkept)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    if (n_models > 256) return fail(SQK_ERR_UNSUPPORTED, "more than 256 models per call");
+    TRY(launch_f64_front(c, s, st, v, p->scale_mode, p->lo, p->hi, 0, 0.0, d_nkept));
+    TRY(ensure(s.counter, 256 * sizeof(unsigned)));
+    CU(cudaMemsetAsync(s.counter.p, 0, 256 * sizeof(unsigned), st));
+    for (int m = 0; m < n_models; m++) {
+        const int N = h_model_offsets[m + 1] - h_model_offsets[m];
+        int L = 0, K = 0;
+        sqk_dtw_launcher fn = nullptr;
+        TRY(pick_dtw(c, N, p->precision, &L, &K, &fn));
+        DtwArgs a{};
+        a.base = nullptr; a.alloc_lo = v.sample0; a.alloc_hi = v.sample0 + v.n_samples;
+        a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+        a.stats = (const ReadStats *)s.stats.p;
+        a.model = d_models + h_model_offsets[m]; a.N = N;
+        a.lo = 0; a.hi = 0;
+        a.hits = d_hits + m; a.hit_stride = n_models;
+        a.counter = (unsigned *)s.counter.p + m;
+        a.prenorm = (const double *)s.ynorm.p - v.sample0;
+        cudaEvent_t eb;
+        TRY(tick(c, SQK_K_DTW, st, &eb));
+        cudaError_t e = fn(K, a, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        TRY(tock(eb, st));
+    }
+    return SQK_OK;
+}
+
+static int enqueue_segmenter_f64(sqk_ctx *c, Slot &s, cudaStream_t st, const View64 &v, const sqk_seg_params *p,
+                                 int32_t *d_segs, int32_t *d_nsegs)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    TRY(launch_f64_front(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr));
+    const double fm = std::ceil((double)p->window * p->stall_len);
+    FsmArgs a{};
+    a.base = (const int16_t *)s.codes.p - v.sample0; a.alloc_lo = v.sample0; a.alloc_hi = v.sample0 + v.n_samples;
+    a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+    a.stats = (const ReadStats *)s.stats.p;
+    a.num = p->num; a.code_rows = 1;
+    a.error = p->error; a.corrector = p->corrector; a.window = p->window; a.seg_dist = p->seg_dist;
+    a.first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
+    a.max_segs = p->max_segs; a.segs = d_segs; a.n_segs = d_nsegs;
+    const unsigned grid = (unsigned)((v.n_reads + SQK_FSM_THREADS - 1) / SQK_FSM_THREADS);
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
+    sqk_fsm_kernel<<<grid, SQK_FSM_THREADS, 0, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+// first and last offset of a device-resident offsets array (one small synchronising copy)
+static int device_sample_range(cudaStream_t st, const int64_t *d_offsets, int64_t n_reads, int64_t *s0, int64_t *s1)
+{
+    CU(cudaMemcpyAsync(s0, d_offsets, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s1, d_offsets + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (*s1 < *s0) return fail(SQK_ERR_ARG, "offsets are not non-decreasing");
+    return SQK_OK;
+}
+
 static int device_max_len(sqk_ctx *c, cudaStream_t st, const int64_t *d_offsets, int64_t n_reads, int64_t *out)
 {
     TRY(ensure(c->scratch8, 8));
@@ -578,7 +676,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
     for (int i = 0; i < 2; i++) {
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
-        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -799,6 +897,112 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
 }
 
 extern "C" {
+
+int sqk_motifseq_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, int64_t n_reads, const double *models,
+                     const int32_t *model_offsets, int32_t n_models, const sqk_motif_params *p, int mem, sqk_hit *hits,
+                     int32_t *n_kept)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_reads < 0) return fail(SQK_ERR_ARG, "n_reads < 0");
+    if (n_reads == 0) return SQK_OK;
+    if (!offsets || !hits) return fail(SQK_ERR_ARG, "offsets/hits is NULL");
+    if (!models || !model_offsets || n_models < 1) return fail(SQK_ERR_ARG, "no models");
+    if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
+    TRY(check_motif_params(p));
+    for (int m = 0; m < n_models; m++)
+        if (model_offsets[m + 1] - model_offsets[m] < 1) return fail(SQK_ERR_ARG, "model %d is empty", m);
+    Guard g(c->device);
+    if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+    const size_t model_bytes = (size_t)model_offsets[n_models] * sizeof(double);
+    TRY(ensure(c->model, model_bytes));
+    if (mem == SQK_MEM_DEVICE) {
+        cudaStream_t st = device_stream(c);
+        if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, st));
+        int64_t s0 = 0, s1 = 0;
+        TRY(device_sample_range(st, offsets, n_reads, &s0, &s1));
+        View64 v{signals, offsets, 0, n_reads, s0, s1 - s0};
+        return enqueue_motifseq_f64(c, c->slot[0], st, v, (const double *)c->model.p, model_offsets, n_models, p, hits, n_kept);
+    }
+    if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
+    for (int64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] < offsets[r]) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
+    CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    std::vector<int64_t> cuts;
+    plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
+    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        Slot &s = c->slot[ci & 1];
+        cudaStream_t st = s.stream;
+        TRY(recycle(s));
+        const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], nr = r1 - r0;
+        const int64_t s0 = offsets[r0], s1 = offsets[r1], ns = s1 - s0;
+        TRY(ensure(s.signals, (size_t)std::max<int64_t>(ns, 2) * sizeof(double)));
+        TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
+        TRY(ensure(s.hits, (size_t)nr * n_models * sizeof(sqk_hit)));
+        TRY(ensure(s.nkept, (size_t)nr * sizeof(int32_t)));
+        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        View64 v{(const double *)s.signals.p - s0, (const int64_t *)s.offsets.p - r0, r0, nr, s0, ns};
+        TRY(enqueue_motifseq_f64(c, s, st, v, (const double *)c->model.p, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
+                                 (int32_t *)s.nkept.p));
+        TRY(result_to_host(s, 0, hits + r0 * n_models, s.hits.p, (size_t)nr * n_models * sizeof(sqk_hit), hits_pinned));
+        if (n_kept) TRY(result_to_host(s, 1, n_kept + r0, s.nkept.p, (size_t)nr * sizeof(int32_t), nkept_pinned));
+    }
+    TRY(recycle(c->slot[0]));
+    TRY(recycle(c->slot[1]));
+    return SQK_OK;
+}
+
+int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, int64_t n_reads,
+                      const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_reads < 0) return fail(SQK_ERR_ARG, "n_reads < 0");
+    if (n_reads == 0) return SQK_OK;
+    if (!offsets || !segs || !n_segs) return fail(SQK_ERR_ARG, "offsets/segs/n_segs is NULL");
+    if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
+    TRY(check_seg_params(p));
+    Guard g(c->device);
+    if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+    const size_t seg_row = (size_t)p->max_segs * 2 * sizeof(int32_t);
+    if (mem == SQK_MEM_DEVICE) {
+        cudaStream_t st = device_stream(c);
+        if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        int64_t s0 = 0, s1 = 0;
+        TRY(device_sample_range(st, offsets, n_reads, &s0, &s1));
+        View64 v{signals, offsets, 0, n_reads, s0, s1 - s0};
+        return enqueue_segmenter_f64(c, c->slot[0], st, v, p, segs, n_segs);
+    }
+    if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
+    for (int64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] < offsets[r]) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
+    std::vector<int64_t> cuts;
+    plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
+    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        Slot &s = c->slot[ci & 1];
+        cudaStream_t st = s.stream;
+        TRY(recycle(s));
+        const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], nr = r1 - r0;
+        const int64_t s0 = offsets[r0], s1 = offsets[r1], ns = s1 - s0;
+        TRY(ensure(s.signals, (size_t)std::max<int64_t>(ns, 2) * sizeof(double)));
+        TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
+        TRY(ensure(s.segs, (size_t)nr * seg_row));
+        TRY(ensure(s.nsegs, (size_t)nr * sizeof(int32_t)));
+        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(s.segs.p, 0, (size_t)nr * seg_row, st));
+        View64 v{(const double *)s.signals.p - s0, (const int64_t *)s.offsets.p - r0, r0, nr, s0, ns};
+        TRY(enqueue_segmenter_f64(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
+        TRY(result_to_host(s, 0, (char *)segs + (size_t)r0 * seg_row, s.segs.p, (size_t)nr * seg_row, segs_pinned));
+        TRY(result_to_host(s, 1, n_segs + r0, s.nsegs.p, (size_t)nr * sizeof(int32_t), nsegs_pinned));
+    }
+    TRY(recycle(c->slot[0]));
+    TRY(recycle(c->slot[1]));
+    return SQK_OK;
+}
 
 int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
                   const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)

@@ -48,6 +48,7 @@ struct DtwArgs {
     sqk_hit *hits;            // hits[i * hit_stride]
     int hit_stride;
     unsigned int *counter;    // work queue head, zeroed before launch
+    const double *prenorm;    // float64 front end: prenorm[offsets[r] + i] = i-th normalised kept sample (else null)
 };
 
 template <typename T> struct DtwNum;
@@ -193,6 +194,22 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
         if (__all_sync(SQK_FULL_MASK, exhausted)) break;   // exhausted implies done; others re-pull above
 
         // ---- refill the rings: raw int16 -> filter -> normalise -> shared memory ---------------
+        if (a.prenorm != nullptr) {
+            // float64 front end (sqk_f64.cuh): the read is already compacted and normalised in a global row
+            for (;;) {
+                const bool want = !done && (wcount < t + S) && (wcount < n);
+                if (!__any_sync(SQK_FULL_MASK, want)) break;
+                if (want) {
+                    const double *row = a.prenorm + begin;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int idx = wcount + l * 8 + e;
+                        if (idx < n) ring[idx & (RC - 1)] = (T)row[idx];
+                    }
+                    wcount = (n - wcount < CH) ? n : wcount + CH;
+                }
+            }
+        } else
         for (;;) {
             const bool want = !done && (wcount < t + S) && (cursor < end);
             if (!__any_sync(SQK_FULL_MASK, want)) break;

@@ -28,6 +28,7 @@ struct FsmArgs {
     int max_segs;
     int32_t *segs;            // [n_reads][max_segs][2]
     int32_t *n_segs;          // [n_reads]
+    int code_rows;            // float64 front end: `base` holds 0/1 code rows of n_kept samples (no truncation here)
 };
 
 __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs a)
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs 
     resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
     const int64_t r = a.read0 + i;
     const int64_t begin = a.offsets[r];
-    const int64_t end = begin + sqk_truncate_len(a.offsets[r + 1] - begin, a.num);
     const ReadStats st = a.stats[i];
+    const int64_t end = begin + (a.code_rows ? (int64_t)st.n_kept : sqk_truncate_len(a.offsets[r + 1] - begin, a.num));
     if (st.flags & SQK_FLAG_TOO_LONG) { a.n_segs[i] = -1; return; }   // longer than the declared max_read_len
     const int seg_lo = st.seg_lo, seg_hi = st.seg_hi, out_lo = st.out_lo, out_hi = st.out_hi;
     int32_t *out = a.segs + (int64_t)i * a.max_segs * 2;

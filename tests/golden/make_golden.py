@@ -199,6 +199,35 @@ def main():
         json.dump({"offset": cal_offset.tolist(), "range": cal_range.tolist(), "digitisation": digitisation,
                    "cases": pa_out}, f)
 
+    # ---- float (pA) signals, the reference's `-s` path: MotifSeq.py:270-298 and segmenter.py:198-211 ----------
+    fsig_i, foff = synth.ragged_reads_np([1800, 900, 2500, 1, 0, 77, 1300, 640], motif80)
+    fsig = np.round((fsig_i.astype(int) + 9.0) * (1456.78 / 8192.0), 2)          # what SquigglePull prints without -r
+    fout = {"signals": fsig, "offsets": foff.astype(np.int64)}
+    for scale in ("zscale", "medmad"):
+        args = refload.Args(scale=scale, scale_hi=300, scale_low=40)
+        st, en, di, kp = [], [], [], []
+        for r in range(foff.size - 1):
+            sig = np.array([float(i) for i in fsig[foff[r]:foff[r + 1]]])       # MotifSeq.py:270
+            sig = ms.scale_outliers(sig, args)
+            kp.append(sig.size)
+            if sig.size == 0 or (scale == "medmad" and np.median(np.abs(sig - np.median(sig))) == 0):
+                st.append(-9); en.append(-9); di.append(np.nan); continue
+            y = numpy_ref.zscale_np(sig) if scale == "zscale" else numpy_ref.medmad_np(sig)
+            t = run_region_multi(ms, args, y, {"m": motif80}, ["m"], [10], "f", "id")
+            f = t.rstrip("\n").split("\t")
+            st.append(int(f[3])); en.append(int(f[4])); di.append(float(f[6]))
+        fout[scale + "_start"] = np.array(st, dtype=np.int32); fout[scale + "_end"] = np.array(en, dtype=np.int32)
+        fout[scale + "_dist"] = np.array(di); fout[scale + "_kept"] = np.array(kp, dtype=np.int32)
+    sargs_f = refload.Args(lim_hi=160, lim_low=30)
+    fsegs = []
+    for r in range(foff.size - 1):
+        sig = np.array(fsig[foff[r]:foff[r + 1]], dtype=float)[:sargs_f.Num]
+        sig = seg.scale_outliers(sig, sargs_f)
+        fsegs.append(seg.get_segs(sig, sargs_f) if sig.size else None)
+    np.savez_compressed(os.path.join(HERE, "float_signal_golden.npz"), **fout)
+    with open(os.path.join(HERE, "float_signal_segs.json"), "w") as f:
+        json.dump({"lim_hi": 160, "lim_low": 30, "segs": fsegs}, f)
+
     # ---- numpy pairwise-sum known answers (pins oracle.np_sum and the CUDA sigma tree) -----
     rng = np.random.default_rng(11)
     sums = {}

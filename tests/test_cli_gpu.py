@@ -89,3 +89,37 @@ def test_segmenter_single_fast5_default_is_pa(golden_dir):
     out, _ = run("segmenter.py", "-i", path, "--single")
     assert out.rstrip("\n") == path + "\t" + ",".join(f"{a},{b}" for a, b in exp["segs_pA"])
     assert exp["segs_pA"] != exp["segs_raw"]
+
+
+def test_clis_accept_float_pa_tsv(golden_dir, tmp_path):
+    """SquigglePull without -r prints pA floats; both tools must give what the reference's float branch gives."""
+    g = np.load(os.path.join(golden_dir, "float_signal_golden.npz"))
+    want_segs = json.load(open(os.path.join(golden_dir, "float_signal_segs.json")))
+    sig, off = g["signals"], g["offsets"]
+    model, exp = write_model(tmp_path, golden_dir)
+    bait = tmp_path / "motif80.tsv"
+    from squigglekit_b200 import synth
+    bait.write_text("m\t10\tx\t" + "\t".join(repr(float(v)) for v in synth.make_motif()) + "\n")
+    ms_tsv, sg_tsv = tmp_path / "ms.tsv", tmp_path / "sg.tsv"
+    with open(ms_tsv, "w") as f1, open(sg_tsv, "w") as f2:
+        for r in range(off.size - 1):
+            vals = [repr(float(v)) for v in sig[off[r]:off[r + 1]]]
+            if not vals:
+                continue
+            f1.write("\t".join([f"read{r}.fast5", f"id{r}"] + ["x"] * 6 + vals) + "\n")
+            f2.write("\t".join([f"read{r}.fast5", "id", "a", "b"] + vals) + "\n")
+    out, _ = run("MotifSeq.py", "-s", str(ms_tsv), "-m", str(bait), "-l", "zscale", "-scale_hi", "300", "-scale_low", "40")
+    rows = {l.split("\t")[0]: l.split("\t") for l in out.rstrip("\n").split("\n")[1:]}
+    for r in range(off.size - 1):
+        if g["zscale_start"][r] == -9 or off[r + 1] == off[r]:
+            continue
+        f = rows[f"read{r}.fast5"]
+        assert (int(f[3]), int(f[4]), f[6]) == (int(g["zscale_start"][r]), int(g["zscale_end"][r]), repr(float(g["zscale_dist"][r])))
+    out, _ = run("segmenter.py", "-s", str(sg_tsv), "-lim_hi", "160", "-lim_low", "30")
+    got = dict(l.split("\t") for l in out.rstrip("\n").split("\n") if l)
+    for r, w in enumerate(want_segs["segs"]):
+        key = f"read{r}.fast5"
+        if w:
+            assert got[key] == ",".join(f"{a},{b}" for a, b in w), r
+        else:
+            assert key not in got

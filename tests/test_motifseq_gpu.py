@@ -338,3 +338,72 @@ def test_understated_max_read_len_is_flagged_not_overrun(ctx):
     assert int(nsegs[1]) == -1
     with pytest.raises(ValueError):
         sqk.segs_to_lists(segs.cpu().numpy(), nsegs.cpu().numpy())
+
+
+# ---- float64 signals: the reference's `-s` path on a TSV of floats ---------------------------
+def test_float_signal_golden(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "float_signal_golden.npz"))
+    motif = synth.make_motif()
+    for scale in ("zscale", "medmad"):
+        hits, kept = ctx.motifseq(g["signals"], g["offsets"], motif, scale=scale, scale_low=40, scale_hi=300)
+        ok = g[scale + "_start"] != -9
+        assert np.array_equal(kept, g[scale + "_kept"])
+        assert np.array_equal(hits["start"][ok, 0], g[scale + "_start"][ok])
+        assert np.array_equal(hits["end"][ok, 0], g[scale + "_end"][ok])
+        assert np.array_equal(hits["dist"][ok, 0], g[scale + "_dist"][ok])
+        assert (hits["start"][~ok, 0] < 0).all()
+    want = json.load(open(os.path.join(golden_dir, "float_signal_segs.json")))
+    segs, nsegs = ctx.segmenter(g["signals"], g["offsets"], sqk.SegConfig(lim_low=want["lim_low"], lim_hi=want["lim_hi"], max_segs=64))
+    got = sqk.segs_to_lists(segs, nsegs)
+    for r, w in enumerate(want["segs"]):
+        assert got[r] == (w if w else False), r
+
+
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_float_signal_vs_oracle(ctx, mode):
+    """Arbitrary doubles (not multiples of 0.01), ragged lengths, negative values, both scalings, both tools."""
+    motif = synth.make_motif()
+    rng = np.random.default_rng(12)
+    lengths = [3000, 0, 1, 2, 9, 4096, 130, 700, 12000, 33]
+    sig_i, off = synth.ragged_reads_np(lengths, motif)
+    sig = (sig_i.astype(np.float64) - 500.0) * 0.1773 + rng.standard_normal(sig_i.size) * 1e-3
+    for scale in ("zscale", "medmad", "none"):
+        want, kept_w = oracle.motifseq_batch_f64(sig, off, motif, lo=-60, hi=90, scale=scale)
+        if mode == "device":
+            import torch
+            h_t, k_t = ctx.motifseq(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), motif, scale=scale, scale_low=-60, scale_hi=90)
+            torch.cuda.synchronize()
+            hits, kept = sqk.hits_from_torch(h_t), k_t.cpu().numpy()
+        else:
+            hits, kept = ctx.motifseq(sig, off, motif, scale=scale, scale_low=-60, scale_hi=90)
+        ok = (kept_w > 0) & np.isfinite(want["dist"])
+        assert np.array_equal(kept, kept_w)
+        assert_hits_equal(hits[ok, 0], want[ok], what=f"f64 {scale}/{mode}")
+        assert (hits["start"][~ok, 0] < 0).all()
+    for params in (dict(), dict(error=80, corrector=0, window=10), dict(Num=1000)):
+        cfg = sqk.SegConfig(lim_low=-60, lim_hi=90, max_segs=256, **params)
+        ocfg = oracle.SegCfg(cfg.error, cfg.corrector, cfg.window, cfg.seg_dist, cfg.std_scale, cfg.stall_len)
+        want_s, want_n = oracle.segmenter_batch_f64(sig, off, ocfg, -60, 90, cfg.Num, 256)
+        if mode == "device":
+            import torch
+            s_t, n_t = ctx.segmenter(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), cfg)
+            torch.cuda.synchronize()
+            segs, nsegs = s_t.cpu().numpy(), n_t.cpu().numpy()
+        else:
+            segs, nsegs = ctx.segmenter(sig, off, cfg)
+        assert np.array_equal(nsegs, want_n), params
+        for r in range(nsegs.size):
+            assert np.array_equal(segs[r, :nsegs[r]], want_s[r, :want_n[r]]), (params, r)
+
+
+def test_float_signal_that_is_integer_valued_matches_int16_path(ctx):
+    """Feeding raw integers as float64 must give exactly what the int16 kernels give."""
+    motif = synth.make_motif()
+    sig, off, _ = synth.motifseq_reads_np(64, 3000, motif)
+    for scale in ("zscale", "medmad"):
+        a, ka = ctx.motifseq(sig, off, motif, scale=scale)
+        b, kb = ctx.motifseq(sig.astype(np.float64), off, motif, scale=scale)
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)) and np.array_equal(ka, kb)
+    s1, n1 = ctx.segmenter(sig, off, sqk.SegConfig())
+    s2, n2 = ctx.segmenter(sig.astype(np.float64), off, sqk.SegConfig())
+    assert np.array_equal(n1, n2) and np.array_equal(s1, s2)
