@@ -64,6 +64,7 @@ def build_parser():
     parser.add_argument("--device", type=int, default=0, help="[sqk] CUDA device index")
     parser.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                         help="[sqk] fp64 = bit-exact with the reference's float64 DTW (default); fp32 = fast mode")
+    group.add_argument("--slow5", help="[sqk] BLOW5 file (binary SLOW5) instead of fast5 / TSV input")
     parser.add_argument("--start_col", type=int, default=8, help="[sqk] first signal column of a -s file (reference: 8)")
     return parser
 
@@ -103,6 +104,11 @@ def iter_reads(args):
                     fast5_file = os.path.join(dirpath, fast5)
                     yield from _one_fast5(f5, fast5_file, fast5,
                                           "main():data not extracted. Moving to next file - {}\n".format(fast5_file))
+    elif args.slow5:
+        from . import slow5
+        name = os.path.basename(args.slow5)
+        for rec in slow5.read_blow5(args.slow5):
+            yield name, rec["read_id"], rec["signal"]
     elif args.signal:
         with _opener(args.signal)(args.signal, 'rt') as s:
             for line in s:
@@ -214,7 +220,7 @@ def main(argv=None):
         sys.exit(1)
     if args.view or args.save:
         sys.stderr.write("warning: -v/--view and --save plotting are not part of the GPU port; printing rows only\n")
-    if not (args.f5f or args.f5_path or args.signal):
+    if not (args.f5f or args.f5_path or args.signal or args.slow5):
         sys.stderr.write("Unknown file or path input")
         parser.print_help(sys.stderr)
         sys.exit(1)

@@ -40,6 +40,7 @@ def build_parser():
     group.add_argument("-i", "--ind", nargs='+', help="Individual fast5 file/s")
     group.add_argument("-p", "--f5_path", help="Fast5 top dir")
     group.add_argument("-s", "--signal", help="Extracted signal file from squigglePull")
+    group.add_argument("--slow5", help="[sqk] BLOW5 file (binary SLOW5) instead of fast5 / TSV input")
     parser.add_argument("--single", action="store_true", help="single fast5 files")
     parser.add_argument("-n", "--Num", type=int, default=0, help="Section of signal to look at - default 0=all")
     parser.add_argument("-e", "--error", type=int, default=5, help="Allowable error in segment algorithm")
@@ -101,6 +102,11 @@ def iter_reads(args):
     elif args.ind:
         for fast5_file in args.ind:
             yield from _fast5_reads(args, fast5_file, fast5_file)
+    elif args.slow5:
+        from . import slow5
+        for rec in slow5.read_blow5(args.slow5):
+            yield (rec["read_id"], rec["signal"], float(rec["offset"]),
+                   float("{0:.2f}".format(rec["range"])) / float(rec["digitisation"]))
     elif args.signal:
         with _opener(args.signal)(args.signal, 'rt') as s:
             from .cli_motifseq import split_signal_columns
@@ -170,7 +176,7 @@ def main(argv=None):
     if not raw_args:
         parser.print_help(sys.stderr)
         sys.exit(1)
-    if not (args.f5_path or args.ind or args.signal):
+    if not (args.f5_path or args.ind or args.signal or args.slow5):
         sys.stderr.write("Unknown file or path input")
         parser.print_help(sys.stderr)
         sys.exit(1)

@@ -123,3 +123,16 @@ def test_clis_accept_float_pa_tsv(golden_dir, tmp_path):
             assert got[key] == ",".join(f"{a},{b}" for a, b in w), r
         else:
             assert key not in got
+
+
+def test_clis_accept_blow5(golden_dir, tmp_path):
+    model, exp = write_model(tmp_path, golden_dir)
+    path = os.path.join(golden_dir, "example.blow5")
+    out, _ = run("MotifSeq.py", "--slow5", path, "-m", model, "-l", "medmad")
+    got = out.rstrip("\n").split("\n")[1].split("\t")
+    want = exp["tsv"]["medmad"].rstrip("\n").split("\t")
+    assert got[1:] == want[1:]
+    out, _ = run("segmenter.py", "--slow5", path)
+    assert out.rstrip("\n").split("\t")[1] == ",".join(f"{a},{b}" for a, b in exp["segs_pA"])
+    out, _ = run("segmenter.py", "--slow5", path, "--raw_signal")
+    assert out.rstrip("\n").split("\t")[1] == ",".join(f"{a},{b}" for a, b in exp["segs_raw"])

@@ -90,3 +90,13 @@ def test_cli_flag_surface_matches_reference():
         (5, 50, 150, 50, 0.75, 0.25, 300, 3000, 900, 0)
     m = cli_motifseq.build_parser().parse_args(["-s", "x", "-m", "y"])
     assert (m.scale, m.slope, m.intercept, m.std_const, m.scale_hi, m.scale_low) == ("medmad", 2.90, -9.6, 0.08468, 1200, 0)
+
+
+def test_blow5_reader_on_the_reference_example(golden_dir):
+    from squigglekit_b200 import slow5
+    recs = list(slow5.read_blow5(os.path.join(golden_dir, "example.blow5")))
+    ex = np.load(os.path.join(golden_dir, "example_read.npz"), allow_pickle=True)
+    assert len(recs) == 1
+    r = recs[0]
+    assert r["read_id"] == str(ex["read_id"]) and np.array_equal(r["signal"], ex["raw"])
+    assert (r["digitisation"], r["offset"], r["sampling_rate"]) == (8192.0, 16.0, 4000.0)
