@@ -20,7 +20,8 @@
  *     mem = SQK_MEM_DEVICE: every pointer is device memory on the ctx's device; the call only
  *                           enqueues work on the ctx stream (sqk_ctx_set_stream / sqk_ctx_sync).
  *   - return value: 0 = ok, <0 = sqk_status; message via sqk_last_error() (thread-local).
- *   - a ctx is bound to one device and is not thread-safe; use one ctx per host thread.
+ *   - a ctx is bound to one device and is not thread-safe; use one ctx per host thread.  Device-mode calls
+ *     share the ctx's scratch memory in stream order: keep them on ONE stream (or sqk_ctx_sync between streams).
  *   - the caller owns every buffer passed in; the library keeps no reference after return
  *     (device mode: after the stream work has completed).
  *   - there is NO CPU fallback: without a CUDA device sqk_ctx_create fails.

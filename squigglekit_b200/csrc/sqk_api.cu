@@ -633,6 +633,24 @@ int sqk_device_count(int *count)
     return SQK_OK;
 }
 
+static int ctx_init(sqk_ctx *c, int device)
+{
+    c->device = device;
+    int v = 0;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); c->n_sms = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)); c->smem_optin = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); c->clock_khz = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device)); c->l2_bytes = v;
+    int maj = 0, min = 0;
+    CU(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, device));
+    c->cc = maj * 10 + min;
+    if (c->cc != 100)
+        return fail(SQK_ERR_UNSUPPORTED, "device %d is sm_%d; libsqk is built for sm_100a (B200) only", device, maj * 10 + min);
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+    return SQK_OK;
+}
+
 int sqk_ctx_create(int device, sqk_ctx **out)
 {
     if (!out) return fail(SQK_ERR_ARG, "out is NULL");
@@ -647,21 +665,12 @@ int sqk_ctx_create(int device, sqk_ctx **out)
     if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     sqk_ctx *c = new (std::nothrow) sqk_ctx();
     if (!c) return fail(SQK_ERR_NOMEM, "out of host memory");
-    c->device = device;
-    int v = 0;
-    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); c->n_sms = v;
-    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)); c->smem_optin = v;
-    CU(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); c->clock_khz = v;
-    CU(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device)); c->l2_bytes = v;
-    int maj = 0, min = 0;
-    CU(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
-    CU(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, device));
-    c->cc = maj * 10 + min;
-    if (c->cc != 100) {
+    const int rc = ctx_init(c, device);
+    if (rc != SQK_OK) {
+        for (int i = 0; i < 2; i++) if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
         delete c;
-        return fail(SQK_ERR_UNSUPPORTED, "device %d is sm_%d; libsqk is built for sm_100a (B200) only", device, maj * 10 + min);
+        return rc;
     }
-    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
     *out = c;
     return SQK_OK;
 }
