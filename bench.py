@@ -132,6 +132,12 @@ def cpu_reference_rate(signals, offsets, motif, threads: int, target_s: float):
     return done / dt, done, dt
 
 
+def bench_motif():
+    """Default: 10 levels x dwell 8 = 80 points; other lengths keep dwell 8 and cut to size."""
+    from squigglekit_b200 import synth
+    return synth.make_motif(n_levels=(N_MOTIF + 7) // 8, dwell=8)[:N_MOTIF]
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path, all host threads, same workload shape."""
     rank = int(os.environ.get("RANK", "0"))
@@ -140,7 +146,7 @@ def run_reference(args):
     import oracle
     from squigglekit_b200 import synth
     threads = oracle.max_threads()
-    motif = synth.make_motif()
+    motif = bench_motif()
     n_gen = 4096 * max(1, min(threads, 16) // 4)
     sig, off, _ = synth.motifseq_reads_np(min(n_gen, N_READS), N_SAMPLES, motif)
     for _ in range(args.warmup):
@@ -195,6 +201,7 @@ def alu_peak_cells_per_s():
 
 
 def main():
+    global N_SAMPLES, N_MOTIF, BYTES_PER_READ, CELLS_PER_READ
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -204,7 +211,13 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="force lanes-per-read of the DTW kernel (experiments)")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (very large batches: it needs the batch in pinned host memory)")
+    ap.add_argument("--samples", type=int, default=4096, help="samples per read (default 4096; 20000 = BASELINE configs[3])")
+    ap.add_argument("--motif-len", type=int, default=80, help="motif points (default 80; 163 = the reference's example model)")
     args = ap.parse_args()
+    N_SAMPLES, N_MOTIF = args.samples, args.motif_len
+    BYTES_PER_READ = 2 * N_SAMPLES + 16
+    CELLS_PER_READ = N_SAMPLES * N_MOTIF
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -224,7 +237,7 @@ def main():
     torch.cuda.set_device(dev)
 
     R, M = args.reads, N_SAMPLES
-    motif = synth.make_motif()
+    motif = bench_motif()
     ctx = sqk.Context(local_rank)
     if args.lanes:
         ctx.set_dtw_lanes(args.lanes)
@@ -285,26 +298,28 @@ def main():
         if world > 1:
             assert gathered.shape[0] == world * R
 
-    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ---------------------
-    h_sig = sqk.pinned_empty(R * M, np.int16)
-    h_sig[:] = sig.cpu().numpy()
+    e2e_value, e2e_steps, h_sig, h_hits = None, 0, None, None
     h_off = off.cpu().numpy()
-    h_hits = sqk.pinned_empty((R, 1), sqk.HIT_DTYPE)
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        ctx.motifseq(h_sig, h_off, motif, scale=SCALE, precision=args.precision, max_read_len=M, out=h_hits, want_kept=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.motifseq(h_sig, h_off, motif, scale=SCALE, precision=args.precision, max_read_len=M, out=h_hits, want_kept=False)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * R * e2e_steps / float(te.item())
-    if rank == 0 and args.precision == "fp64":
-        parity["e2e_matches_device_path"] = bool(np.array_equal(h_hits.view(np.uint8).reshape(R, 16), hits.cpu().numpy().reshape(R, 16)))
+    if not args.no_e2e:
+        # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ---------------------
+        h_sig = sqk.pinned_empty(R * M, np.int16)
+        h_sig[:] = sig.cpu().numpy()
+        h_hits = sqk.pinned_empty((R, 1), sqk.HIT_DTYPE)
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            ctx.motifseq(h_sig, h_off, motif, scale=SCALE, precision=args.precision, max_read_len=M, out=h_hits, want_kept=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.motifseq(h_sig, h_off, motif, scale=SCALE, precision=args.precision, max_read_len=M, out=h_hits, want_kept=False)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * R * e2e_steps / float(te.item())
+        if rank == 0 and args.precision == "fp64":
+            parity["e2e_matches_device_path"] = bool(np.array_equal(h_hits.view(np.uint8).reshape(R, 16), hits.cpu().numpy().reshape(R, 16)))
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -332,7 +347,7 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": {"workload": f"MotifSeq {N_MOTIF}-point motif vs {R} synthetic {M}-sample int16 reads per GPU "
-                                   f"(BASELINE configs[2]); zscale; outlier window (0,1200)",
+                                   f"(BASELINE configs[2] when 100000 x 4096 x 80); zscale; outlier window (0,1200)",
                        "reads_per_gpu": R, "n_samples": M, "n_motif": N_MOTIF, "scale": SCALE, "precision": args.precision,
                        "l2_policy": f"input {R * M * 2 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks; e2e = wall clock of the synchronous host-buffer C-ABI call",
@@ -347,14 +362,15 @@ def main():
                              "frac": (cells_s / alu_peak) if alu_peak else None, "peak_source": alu_src},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(R * M * 2 + (R + 1) * 8),
-                    "d2h_bytes_per_step": int(R * 16), "steps": e2e_steps},
+            "e2e": ({"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(R * M * 2 + (R + 1) * 8),
+                     "d2h_bytes_per_step": int(R * 16), "steps": e2e_steps} if e2e_value is not None else None),
             "gpu_launches": int(kt["dtw"]["launches"] + kt["stats"]["launches"]),
             "parity": parity,
         }
         print(json.dumps(line), flush=True)
-    sqk.pinned_free(h_sig)
-    sqk.pinned_free(h_hits)
+    if h_sig is not None:
+        sqk.pinned_free(h_sig)
+        sqk.pinned_free(h_hits)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -377,10 +377,10 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
         for (int li = 0; li < 5; li++) if (lanes[li] == c->force_lanes && fits(li)) pick = li;
         if (pick < 0) return fail(SQK_ERR_UNSUPPORTED, "motif of %d points cannot run with %d lanes per read", N, c->force_lanes);
     } else {
-        // default policy (measured on B200, profiles/): about 10 motif rows per lane keeps the kernel at
+        // default policy (measured on B200, profiles/): 10-12 motif rows per lane keep the kernel at
         // <= 110 registers (4+ CTAs per SM) while one shuffle still pays for 10 cells; beyond 320 points
         // every lane is in use and the rows per lane grow instead.
-        const int want_k = 10;
+        const int want_k = 12;
         for (int li = 0; li < 5 && pick < 0; li++)
             if (fits(li) && (N + lanes[li] - 1) / lanes[li] <= want_k) pick = li;
         for (int li = 0; li < 5 && pick < 0; li++)
