@@ -64,15 +64,23 @@ __device__ __forceinline__ int4 ld_stream_16(const void *p)
     return r;
 }
 
+// Cached 16-byte load (the line stays in L1: for kernels whose lanes each walk their own read, so that the
+// other half of every 32-byte sector -- and the rest of the 128-byte line -- is not fetched from L2/HBM again).
+__device__ __forceinline__ int4 ld_cached_16(const void *p)
+{
+    return __ldg(reinterpret_cast<const int4 *>(p));
+}
+
 // Load the 8-sample block starting at sample index `blk` (absolute index into the signal
 // array whose element 0 is at `base`); `blk` is such that the address is 16-byte aligned.
 // Blocks that stick out of the allocation [alloc_lo, alloc_hi) are read sample by sample.
+template <bool STREAM = true>
 __device__ __forceinline__ Samples8 load_block8(const int16_t *base, int64_t blk, int64_t alloc_lo,
                                                 int64_t alloc_hi)
 {
     Samples8 s;
     if (blk >= alloc_lo && blk + 8 <= alloc_hi) {
-        s.v = ld_stream_16(base + blk);
+        s.v = STREAM ? ld_stream_16(base + blk) : ld_cached_16(base + blk);
     } else {
         int w[4] = {0, 0, 0, 0};
 #pragma unroll

@@ -50,38 +50,49 @@ __global__ void __launch_bounds__(SQK_FSM_THREADS) sqk_fsm_kernel(const FsmArgs 
     int start = 0, pos = 0, nseg = 0;
     int last_start = 0, last_end = 0;
 
-    for (int64_t blk = aligned_block_start(a.base, begin); blk < end; blk += 8) {
-        const Samples8 smp = load_block8(a.base, blk, alloc_lo, alloc_hi);
+    // Each lane streams its own read 16 bytes at a time through L1 (cached loads: the other half of the 32-byte
+    // sector and the rest of the 128-byte line are L1 hits, so HBM traffic stays at the algorithmic bytes); the
+    // next block is requested before the current one is consumed.
+    int64_t blk = aligned_block_start(a.base, begin);
+    Samples8 cur;
+    if (blk < end) cur = load_block8<false>(a.base, blk, alloc_lo, alloc_hi);
+    for (; blk < end; blk += 8) {
+        Samples8 nxt;
+        if (blk + 8 < end) nxt = load_block8<false>(a.base, blk + 8, alloc_lo, alloc_hi);
+        {
+            const Samples8 smp = cur;
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int64_t idx = blk + e;
-            const int v = smp.get(e);
-            if (idx < begin || idx >= end || v < out_lo || v > out_hi) continue;   // scale_outliers
-            if (v >= seg_lo && v <= seg_hi) {
-                if (!open) { start = pos; open = true; }
-                c++; w++;
-                run_err = 0;
-                if (c >= a.window && c >= w && (c % w) == 0) err--;
-            } else if (open) {
-                if (err < a.error) {
-                    c++; err++; run_err++;
+            for (int e = 0; e < 8; e++) {
+                const int64_t idx = blk + e;
+                const int v = smp.get(e);
+                if (idx < begin || idx >= end || v < out_lo || v > out_hi) continue;   // scale_outliers
+                if (v >= seg_lo && v <= seg_hi) {
+                    if (!open) { start = pos; open = true; }
+                    c++; w++;
+                    run_err = 0;
                     if (c >= a.window && c >= w && (c % w) == 0) err--;
-                } else {
-                    if (c >= a.window || (nseg == 0 && c >= a.first_min)) {
-                        const int stop = pos - run_err;
-                        if (nseg > 0 && start - last_end < a.seg_dist) {
-                            last_end = stop;
-                        } else {
-                            nseg++;
-                            last_start = start; last_end = stop;
+                } else if (open) {
+                    if (err < a.error) {
+                        c++; err++; run_err++;
+                        if (c >= a.window && c >= w && (c % w) == 0) err--;
+                    } else {
+                        if (c >= a.window || (nseg == 0 && c >= a.first_min)) {
+                            const int stop = pos - run_err;
+                            if (nseg > 0 && start - last_end < a.seg_dist) {
+                                last_end = stop;
+                            } else {
+                                nseg++;
+                                last_start = start; last_end = stop;
+                            }
+                            if (nseg <= a.max_segs) { out[2 * (nseg - 1)] = last_start; out[2 * (nseg - 1) + 1] = last_end; }
                         }
-                        if (nseg <= a.max_segs) { out[2 * (nseg - 1)] = last_start; out[2 * (nseg - 1) + 1] = last_end; }
+                        open = false; c = 0; err = 0; run_err = 0;
                     }
-                    open = false; c = 0; err = 0; run_err = 0;
                 }
+                pos++;
             }
-            pos++;
         }
+        cur = nxt;
     }
     a.n_segs[i] = nseg;
 }
