@@ -54,7 +54,7 @@ struct StatsArgs {
 
 struct StatsShared {
     union {                                           // the three users never overlap in time
-        uint32_t hist[SQK_HIST_BINS];                 // median / MAD histogram, then its prefix sums
+        uint32_t hist[SQK_HIST_BINS + SQK_HIST_BINS / 32];   // median / MAD histogram, then its prefix sums (padded, see HB)
         struct {
             int off[SQK_HEAP_NODES], len[SQK_HEAP_NODES];
             double sum[SQK_HEAP_NODES];
@@ -223,19 +223,23 @@ __device__ __forceinline__ double stats_sum(Term term, int n, StatsShared &sh)
     return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap<NT>(term, n, sh) : stats_pairwise<NT>(term, n, sh);
 }
 
+// direct-histogram bins are padded by one word per 32 so that the per-thread runs of consecutive bins in the
+// prefix scan fall into different shared-memory banks
+#define HB(b) ((b) + ((b) >> 5))
+
 // ---- order statistics from a direct histogram of the raw values (window of <= SQK_HIST_BINS values) ----
 // After stats_histogram, sh.hist[b] = number of staged samples with value <= base + b (inclusive prefix).
 template <int NT>
 __device__ void stats_histogram(const int16_t *stage, int n, int base, StatsShared &sh)
 {
     const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;
-    for (int b = tid; b < SQK_HIST_BINS; b += NT) sh.hist[b] = 0;
+    for (int b = tid; b < SQK_HIST_BINS + SQK_HIST_BINS / 32; b += NT) sh.hist[b] = 0;
     stats_sync<NT>();
-    for (int i = tid; i < n; i += NT) atomicAdd(&sh.hist[(int)stage[i] - base], 1u);
+    for (int i = tid; i < n; i += NT) atomicAdd(&sh.hist[HB((int)stage[i] - base)], 1u);
     stats_sync<NT>();
     constexpr int PER = SQK_HIST_BINS / NT;      // consecutive bins per thread
     uint32_t run = 0;
-    for (int q = 0; q < PER; q++) run += sh.hist[tid * PER + q];
+    for (int q = 0; q < PER; q++) run += sh.hist[HB(tid * PER + q)];
     uint32_t incl = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -250,8 +254,8 @@ __device__ void stats_histogram(const int16_t *stage, int n, int base, StatsShar
     if (NT > 32)
         for (int w = 0; w < warp; w++) acc += sh.scan_part[w];
     for (int q = 0; q < PER; q++) {
-        acc += sh.hist[tid * PER + q];
-        sh.hist[tid * PER + q] = acc;
+        acc += sh.hist[HB(tid * PER + q)];
+        sh.hist[HB(tid * PER + q)] = acc;
     }
     stats_sync<NT>();
 }
@@ -262,7 +266,7 @@ __device__ __forceinline__ int stats_hist_select(const StatsShared &sh, int nbin
     int lo = 0, hi = nbins - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (sh.hist[mid] > (uint32_t)rank) hi = mid; else lo = mid + 1;
+        if (sh.hist[HB(mid)] > (uint32_t)rank) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
@@ -278,7 +282,7 @@ __device__ __forceinline__ int stats_hist_within(const StatsShared &sh, int base
     if (ihi >= nbins) ihi = nbins - 1;
     if (ilo < 0) ilo = 0;
     if (ihi < ilo) return 0;
-    return (int)(sh.hist[ihi] - (ilo > 0 ? sh.hist[ilo - 1] : 0u));
+    return (int)(sh.hist[HB(ihi)] - (ilo > 0 ? sh.hist[HB(ilo - 1)] : 0u));
 }
 
 // rank-th smallest doubled distance |2v - med2|
