@@ -362,7 +362,7 @@ __device__ __forceinline__ int stats_last_below(double limit, double off, double
 }
 
 template <int NT>
-__global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const StatsArgs a)
+__global__ void __launch_bounds__(SQK_STATS_THREADS, 6) sqk_stats_kernel(const StatsArgs a)
 {
     constexpr int GROUPS = SQK_STATS_THREADS / NT;
     constexpr int WARPS = NT / 32;
@@ -415,6 +415,8 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
         // ---- pass over HBM: filter, compact, integer sum ------------------------------------
         long long sum = 0;
         int total = 0;
+        const bool window_ok = out_hi >= out_lo;
+        const unsigned span = (unsigned)(out_hi - out_lo);
         const int64_t blk0 = aligned_block_start(a.base, begin);
         constexpr int U = 4;                      // 16-byte loads in flight per thread
         for (int64_t cb = blk0; cb < end; cb += (int64_t)NT * 8 * U) {
@@ -431,12 +433,25 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS) sqk_stats_kernel(const Stat
                 const Samples8 s = sv[u];
                 unsigned keep = 0;
                 if (blk < end && blk + 8 > begin) {
+                    // one unsigned compare per sample for the window; edge blocks mask the samples outside the read
+                    int lsum = 0;
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         const int v = s.get(e);
-                        const int64_t idx = blk + e;
-                        if (idx >= begin && idx < end && v >= out_lo && v <= out_hi) { keep |= 1u << e; sum += v; }
+                        if ((unsigned)(v - out_lo) <= span) { keep |= 1u << e; lsum += v; }
                     }
+                    if (blk < begin || blk + 8 > end) {
+                        const int first = blk < begin ? (int)(begin - blk) : 0;
+                        const int last = blk + 8 > end ? (int)(end - blk) : 8;          // valid samples: [first, last)
+                        const unsigned valid = ((1u << last) - 1u) & ~((1u << first) - 1u);
+                        const unsigned drop = keep & ~valid;
+                        keep &= valid;
+#pragma unroll
+                        for (int e = 0; e < 8; e++)
+                            if (drop & (1u << e)) lsum -= s.get(e);
+                    }
+                    if (!window_ok) { keep = 0; lsum = 0; }
+                    sum += lsum;
                 }
                 const int cnt = __popc(keep);
                 int incl = cnt;
