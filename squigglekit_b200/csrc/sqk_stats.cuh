@@ -475,9 +475,21 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS, 6) sqk_stats_kernel(const S
                     }
                 }
                 if (staged && keep) {
+                    if (in_smem) {
+                        // shared-memory window: a fully kept block landing on an even position goes out as four words
+                        if (keep == 0xffu && !(pos & 1)) {
+                            uint32_t *w32 = reinterpret_cast<uint32_t *>(smem_stage + pos);
+                            w32[0] = (uint32_t)s.v.x; w32[1] = (uint32_t)s.v.y; w32[2] = (uint32_t)s.v.z; w32[3] = (uint32_t)s.v.w;
+                        } else {
 #pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+                            for (int e = 0; e < 8; e++)
+                                if (keep & (1u << e)) smem_stage[pos++] = (int16_t)s.get(e);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++)
+                            if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+                    }
                 }
                 total += all;
                 if (NT > 32) __syncthreads();
