@@ -11,9 +11,9 @@
 //
 //   zscale    mean = sum/n (integer sum: exact, order-free);  sd = sqrt(S/n) with S = the sum of
 //             fl(fl(x-mean)^2) taken in numpy's pairwise order: 8-lane teams own the <=128-element
-//             leaves (one lane per strided accumulator, xor-butterfly = numpy's fold); the split tree is
-//             built and folded level by level at heap indices (n <= 8192) or walked depth-first (longer)
-//             -> same bits as sklearn.preprocessing.scale / np.std.
+//             leaves (one lane per strided accumulator, xor-butterfly = numpy's fold); subtrees of <= 8192
+//             elements are built and folded level by level at heap indices, the levels above them are walked
+//             depth-first -> same bits as sklearn.preprocessing.scale / np.std.
 //   medmad    median and MAD from ONE shared-memory histogram of the raw values + prefix scan when the
 //             outlier window spans <= 2048 values (MAD by binary search on count(|2v - 2med| <= D)),
 //             else by two-pass radix select: exact, including the x.5 medians of even-length reads.
@@ -27,8 +27,7 @@
 #include "sqk_common.cuh"
 
 #define SQK_STATS_THREADS 128       // CTA size; a read is owned by NT = 32 or 128 of them
-#define SQK_LEAF_BATCH 64
-#define SQK_TREE_DEPTH 48
+#define SQK_TREE_DEPTH 24
 #define SQK_HIST_BINS 2048          // direct histogram when the outlier window spans <= 2048 raw values
 #define SQK_RADIX_BINS 512          // fallback two-pass radix select (9 + 8 bits)
 #define SQK_HEAP_NODES 256          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
@@ -53,26 +52,17 @@ struct StatsArgs {
 };
 
 struct StatsShared {
-    union {                                           // the three users never overlap in time
+    union {                                           // the two users never overlap in time
         uint32_t hist[SQK_HIST_BINS + SQK_HIST_BINS / 32];   // median / MAD histogram, then its prefix sums (padded, see HB)
         struct {
             int off[SQK_HEAP_NODES], len[SQK_HEAP_NODES];
             double sum[SQK_HEAP_NODES];
         } hp;                                         // heap-indexed pairwise tree (n <= SQK_HEAP_MAX_N)
-        struct {
-            int st_off[SQK_TREE_DEPTH], st_len[SQK_TREE_DEPTH], st_dep[SQK_TREE_DEPTH];
-            int lf_off[SQK_LEAF_BATCH], lf_len[SQK_LEAF_BATCH], lf_dep[SQK_LEAF_BATCH];
-            double lf_sum[SQK_LEAF_BATCH];
-            double cs_val[SQK_TREE_DEPTH];
-            int cs_dep[SQK_TREE_DEPTH];
-            int sp, csp, nleaf;
-        } wk;                                         // serial depth-first walk (longer reads)
     };
     unsigned long long sum_part[4];
     int warp_tot[4];
     uint32_t scan_part[4];
     uint32_t sel[2];
-    double result;
 };
 
 // barrier over the NT threads that own a read
@@ -103,66 +93,6 @@ __device__ __forceinline__ double stats_leaf_sum(Term term, int off, int len, in
     r = __dadd_rn(r, shfl_xor_f64(r, 4, 8));
     for (int i = body; i < len; i++) r = __dadd_rn(r, term(off + i));
     return r;
-}
-
-// np.sum over term(0..n-1) in numpy's pairwise order, any n: serial depth-first walk by one thread, leaves in
-// batches by the teams, leaf sums folded with a depth stack.  Result valid in every thread of the group.
-template <int NT, class Term>
-__device__ double stats_pairwise(Term term, int n, StatsShared &sh)
-{
-    const int tid = threadIdx.x % NT;
-    constexpr int TEAMS = NT / 8;
-    if (tid == 0) {
-        sh.wk.st_off[0] = 0; sh.wk.st_len[0] = n; sh.wk.st_dep[0] = 0;
-        sh.wk.sp = 1; sh.wk.csp = 0;
-    }
-    stats_sync<NT>();
-    for (;;) {
-        if (tid == 0) {
-            // resume the depth-first walk: emit the next batch of leaves in numpy's evaluation order
-            int sp = sh.wk.sp, nl = 0;
-            while (sp > 0 && nl < SQK_LEAF_BATCH) {
-                sp--;
-                const int off = sh.wk.st_off[sp], len = sh.wk.st_len[sp], dep = sh.wk.st_dep[sp];
-                if (len <= 128) {
-                    sh.wk.lf_off[nl] = off; sh.wk.lf_len[nl] = len; sh.wk.lf_dep[nl] = dep; nl++;
-                } else {
-                    int h = len / 2;
-                    h -= h % 8;
-                    sh.wk.st_off[sp] = off + h; sh.wk.st_len[sp] = len - h; sh.wk.st_dep[sp] = dep + 1; sp++;   // right, popped later
-                    sh.wk.st_off[sp] = off; sh.wk.st_len[sp] = h; sh.wk.st_dep[sp] = dep + 1; sp++;             // left, popped next
-                }
-            }
-            sh.wk.sp = sp; sh.wk.nleaf = nl;
-        }
-        stats_sync<NT>();
-        const int nl = sh.wk.nleaf;
-        if (nl == 0) break;
-        const int team = tid >> 3, k = tid & 7;
-        for (int q = team; q < ((nl + TEAMS - 1) / TEAMS) * TEAMS; q += TEAMS) {
-            // whole warps stay converged for the shuffles; surplus teams redo the last leaf
-            const int qq = q < nl ? q : nl - 1;
-            const double s = stats_leaf_sum(term, sh.wk.lf_off[qq], sh.wk.lf_len[qq], k);
-            if (q < nl && k == 0) sh.wk.lf_sum[q] = s;
-        }
-        stats_sync<NT>();
-        if (tid == 0) {
-            int csp = sh.wk.csp;
-            for (int q = 0; q < nl; q++) {
-                double v = sh.wk.lf_sum[q];
-                int dep = sh.wk.lf_dep[q];
-                while (csp > 0 && sh.wk.cs_dep[csp - 1] == dep) {   // sibling on the stack: left + right
-                    v = __dadd_rn(sh.wk.cs_val[csp - 1], v);
-                    dep--; csp--;
-                }
-                sh.wk.cs_val[csp] = v; sh.wk.cs_dep[csp] = dep; csp++;
-            }
-            sh.wk.csp = csp;
-            if (sh.wk.sp == 0) sh.result = sh.wk.cs_val[0];
-        }
-        stats_sync<NT>();
-    }
-    return sh.result;
 }
 
 // Same sum, tree built and folded in parallel: nodes live at heap indices (root 1, children 2h and 2h+1),
@@ -217,10 +147,44 @@ __device__ double stats_pairwise_heap(Term term, int n, StatsShared &sh)
     return r;
 }
 
+// np.sum over term(0..n-1) in numpy's pairwise order, any n.  numpy's recursion applies the same rule to every
+// subtree, so each subtree of <= SQK_HEAP_MAX_N elements is summed by the parallel heap routine and the few levels
+// above are walked depth-first and folded with a depth stack -- identically in every thread of the group (the
+// control flow depends on n only), so the collective calls inside stay converged.
+template <int NT, class Term>
+__device__ __noinline__ double stats_sum_long(Term term, int n, StatsShared &sh)
+{
+    int st_off[SQK_TREE_DEPTH], st_len[SQK_TREE_DEPTH], st_dep[SQK_TREE_DEPTH], cs_dep[SQK_TREE_DEPTH];
+    double cs_val[SQK_TREE_DEPTH];
+    int sp = 1, csp = 0;
+    st_off[0] = 0; st_len[0] = n; st_dep[0] = 0;
+    while (sp > 0) {
+        sp--;
+        const int off = st_off[sp], len = st_len[sp];
+        int dep = st_dep[sp];
+        if (len <= SQK_HEAP_MAX_N) {
+            auto sub = [term, off](int q) -> double { return term(off + q); };
+            double v = stats_pairwise_heap<NT>(sub, len, sh);
+            while (csp > 0 && cs_dep[csp - 1] == dep) {          // sibling on the stack: left + right
+                v = __dadd_rn(cs_val[csp - 1], v);
+                dep--; csp--;
+            }
+            cs_val[csp] = v; cs_dep[csp] = dep; csp++;
+        } else {
+            int h = len / 2;
+            h -= h % 8;
+            st_off[sp] = off + h; st_len[sp] = len - h; st_dep[sp] = dep + 1; sp++;   // right, popped later
+            st_off[sp] = off; st_len[sp] = h; st_dep[sp] = dep + 1; sp++;             // left, popped next
+        }
+    }
+    return cs_val[0];
+}
+
 template <int NT, class Term>
 __device__ __forceinline__ double stats_sum(Term term, int n, StatsShared &sh)
 {
-    return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap<NT>(term, n, sh) : stats_pairwise<NT>(term, n, sh);
+    // the long-read walk keeps its little stacks in local memory: out of line, so the common path has no frame
+    return n <= SQK_HEAP_MAX_N ? stats_pairwise_heap<NT>(term, n, sh) : stats_sum_long<NT>(term, n, sh);
 }
 
 // direct-histogram bins are padded by one word per 32 so that the per-thread runs of consecutive bins in the
