@@ -174,7 +174,7 @@ def run_reference(args):
     return 0
 
 
-def alu_peak_cells_per_s():
+def alu_peak_cells_per_s(which="dtw_step", prec="fp64"):
     """Register-only micro-benchmark of the DTW step's instruction mix (squigglekit_b200/sqk_ubench):
     the ALU roofline of the kernel.  Falls back to the committed measurement in profiles/."""
     exe = os.path.join(ROOT, "squigglekit_b200", "sqk_ubench")
@@ -195,7 +195,7 @@ def alu_peak_cells_per_s():
             d = json.loads(ln)
         except Exception:
             continue
-        if d.get("bench") == "dtw_step" and d.get("precision") == "fp64":
+        if d.get("bench") == which and d.get("precision") == prec:
             best = max(best or 0.0, float(d["cells_per_s"]))
     return best, src
 
@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU per step (default: BASELINE configs[2])")
     ap.add_argument("--lanes", type=int, default=0, help="force lanes-per-read of the DTW kernel (experiments)")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--plan", default="auto", choices=["auto", "single_pass", "two_pass"],
+                    help="how exact (fp64) requests run: float64 recurrence over every column, or float32 lower-bound scan + float64 windows (same bits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (very large batches: it needs the batch in pinned host memory)")
     ap.add_argument("--samples", type=int, default=4096, help="samples per read (default 4096; 20000 = BASELINE configs[3])")
@@ -241,6 +243,7 @@ def main():
     ctx = sqk.Context(local_rank)
     if args.lanes:
         ctx.set_dtw_lanes(args.lanes)
+    ctx.set_dtw_plan(args.plan)
     sig = synth.motifseq_reads_torch(R, M, motif, dev, seed=synth.BASE_SEED + rank).view(-1)
     off = torch.arange(R + 1, dtype=torch.int64, device=dev) * M
     hits = torch.empty((R, 1, 16), dtype=torch.uint8, device=dev)
@@ -272,6 +275,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     kt = ctx.timing(reset=True)
     ctx.enable_timing(False)
+    plan_counters = ctx.plan_counters()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,15 +327,21 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        dtw_launches = max(1, kt["dtw"]["launches"])
-        dtw_ms = kt["dtw"]["ms"] / dtw_launches
+        two_pass = kt["dtw_lb"]["launches"] > 0
+        if two_pass:
+            # dominant kernel: the float32 lower-bound scan (every sample of every read goes through it once)
+            kname, kkey, ub, ubp = "sqk_dtw_lb_kernel", "dtw_lb", "lb_step", "fp32_rd"
+        else:
+            kname, kkey, ub, ubp = "sqk_dtw_kernel", "dtw", "dtw_step", "fp64" if args.precision == "fp64" else "fp32"
+        dtw_launches = max(1, kt[kkey]["launches"])
+        dtw_ms = kt[kkey]["ms"] / dtw_launches
         achieved = R * BYTES_PER_READ / (dtw_ms * 1e-3) / 1e9
-        alu_peak, alu_src = alu_peak_cells_per_s()
+        alu_peak, alu_src = alu_peak_cells_per_s(ub, ubp)
         cells_s = R * CELLS_PER_READ / (dtw_ms * 1e-3)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "dtw_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch_100k_reads")
+                traffic = json.load(f).get("dram_bytes_per_launch_100k_reads_lb" if two_pass else "dram_bytes_per_launch_100k_reads")
         except Exception:
             pass
         cpu = None
@@ -352,19 +362,24 @@ def main():
                        "l2_policy": f"input {R * M * 2 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks; e2e = wall clock of the synchronous host-buffer C-ABI call",
                        "exchange": "one all-gather of 16-byte hit records per step" if world > 1 else "none (1 GPU)",
-                       "dtw_lanes_per_read": args.lanes or "auto"},
+                       "dtw_lanes_per_read": args.lanes or "auto", "dtw_plan": args.plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "sqk_dtw_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                          "kernel_ms_per_launch": dtw_ms, "algorithmic_bytes_per_read": BYTES_PER_READ,
                          "note": "the DTW recurrence is ALU-issue bound (SURVEY F7): see roofline_alu",
-                         "stats_kernel_ms_per_launch": kt["stats"]["ms"] / max(1, kt["stats"]["launches"])},
+                         "stats_kernel_ms_per_launch": kt["stats"]["ms"] / max(1, kt["stats"]["launches"]),
+                         "exact_windows_ms_per_step": (kt["dtw_win"]["ms"] / max(1, kt["dtw_win"]["launches"])) if two_pass else None},
+            "plan": {"name": "two_pass" if two_pass else "single_pass",
+                     "exact_windows_per_step": plan_counters["windows"] if two_pass else None,
+                     "full_length_fallback_reads_per_step": plan_counters["fallback_reads"] if two_pass else None},
             "roofline_alu": {"achieved_cells_per_s": cells_s, "peak_cells_per_s": alu_peak,
                              "frac": (cells_s / alu_peak) if alu_peak else None, "peak_source": alu_src},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "e2e": ({"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(R * M * 2 + (R + 1) * 8),
                      "d2h_bytes_per_step": int(R * 16), "steps": e2e_steps} if e2e_value is not None else None),
-            "gpu_launches": int(kt["dtw"]["launches"] + kt["stats"]["launches"]),
+            # stats + DTW kernels timed by the library; the two-pass plan launches 3 kernels (windows, finalize, fallback) behind its "dtw_win" timer
+            "gpu_launches": int(kt["dtw"]["launches"] + kt["stats"]["launches"] + kt["dtw_lb"]["launches"] + 3 * kt["dtw_win"]["launches"]),
             "parity": parity,
         }
         print(json.dumps(line), flush=True)

@@ -173,7 +173,14 @@ SQK_API int sqk_segmenter_f64(sqk_ctx *ctx, const double *signals, const int64_t
  * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the
  * launching stream around each launch.  Off by default.  Reading the counters synchronises.
  * ------------------------------------------------------------------------------------- */
-enum sqk_kernel_id { SQK_K_STATS = 0, SQK_K_DTW = 1, SQK_K_SEG_FSM = 2, SQK_K_COUNT = 3 };
+enum sqk_kernel_id {
+    SQK_K_STATS = 0,
+    SQK_K_DTW = 1,      /* single-pass float64 / float32 DTW kernel */
+    SQK_K_SEG_FSM = 2,
+    SQK_K_DTW_LB = 3,   /* two-pass plan, pass 1: float32 lower-bound scan of every read */
+    SQK_K_DTW_WIN = 4,  /* two-pass plan, pass 2: exact float64 windows + finalize + full-length fallback */
+    SQK_K_COUNT = 5
+};
 typedef struct {
     int64_t launches[SQK_K_COUNT];
     double ms[SQK_K_COUNT];
@@ -186,6 +193,18 @@ SQK_API int sqk_ctx_get_timing(sqk_ctx *ctx, sqk_timing *out, int reset);
  * are 1/4 and 1/2 of it). */
 SQK_API int sqk_ctx_set_chunk_samples(sqk_ctx *ctx, int64_t samples);
 SQK_API int sqk_ctx_set_dtw_lanes(sqk_ctx *ctx, int lanes);
+
+/* How SQK_PREC_FP64 requests of sqk_motifseq are executed -- the results are identical bit for bit:
+ *   SINGLE_PASS  the float64 recurrence with start pointers over every column of every read;
+ *   TWO_PASS     a float32, rounded-down, cost-only scan proves which columns can hold mlpy's
+ *                np.argmin(cost[-1, :]) (MotifSeq.py:437-439); the float64 recurrence then runs only on
+ *                windows around those columns, and on the whole read whenever the proof does not close;
+ *   AUTO         TWO_PASS when the longest read is at least 4 windows long (default). */
+enum sqk_dtw_plan { SQK_PLAN_AUTO = 0, SQK_PLAN_SINGLE_PASS = 1, SQK_PLAN_TWO_PASS = 2 };
+SQK_API int sqk_ctx_set_dtw_plan(sqk_ctx *ctx, int plan);
+/* Diagnostics of the most recent two-pass launch of slot 0 (device-mode calls; the last chunk in host mode), first
+ * model: out[0] = exact windows run, out[1] = reads re-run over their full length.  Synchronises. */
+SQK_API int sqk_ctx_get_plan_counters(sqk_ctx *ctx, int64_t out[2]);
 
 #ifdef __cplusplus
 }

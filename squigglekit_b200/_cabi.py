@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libsqk.so")
 SQK_MEM_HOST, SQK_MEM_DEVICE = 0, 1
 SCALE = {"zscale": 0, "medmad": 1, "none": 2}
 PRECISION = {"fp64": 0, "fp32": 1}
-K_STATS, K_DTW, K_SEG_FSM, K_COUNT = 0, 1, 2, 3
+K_STATS, K_DTW, K_SEG_FSM, K_DTW_LB, K_DTW_WIN, K_COUNT = 0, 1, 2, 3, 4, 5
+DTW_PLAN = {"auto": 0, "single_pass": 1, "two_pass": 2}
 
 # sqk_hit: {int32 start; int32 end; double dist}
 HIT_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("dist", "<f8")], align=True)
@@ -46,7 +47,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sqk_version", "sqk_last_error", "sqk_ctx_create", "sqk_ctx_destroy", "sqk_ctx_set_stream", "sqk_ctx_sync",
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
-    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples",
+    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
 ]
 
 _lib = None
@@ -83,6 +84,8 @@ def lib() -> C.CDLL:
     L.sqk_ctx_get_timing.argtypes = [vp, C.POINTER(Timing), C.c_int]
     L.sqk_ctx_set_dtw_lanes.argtypes = [vp, C.c_int]
     L.sqk_ctx_set_chunk_samples.argtypes = [vp, i64]
+    L.sqk_ctx_set_dtw_plan.argtypes = [vp, C.c_int]
+    L.sqk_ctx_get_plan_counters.argtypes = [vp, C.POINTER(i64)]
     for name in EXPORTS:
         if name not in ("sqk_version", "sqk_last_error"):
             getattr(L, name).restype = C.c_int

@@ -106,11 +106,22 @@ class Context:
     def timing(self, reset: bool = True) -> dict:
         t = _cabi.Timing()
         _cabi.check(self._lib.sqk_ctx_get_timing(self._h, C.byref(t), int(reset)))
-        names = ["stats", "dtw", "seg_fsm"]
+        names = ["stats", "dtw", "seg_fsm", "dtw_lb", "dtw_win"]
         return {n: {"launches": int(t.launches[i]), "ms": float(t.ms[i])} for i, n in enumerate(names)}
 
     def set_dtw_lanes(self, lanes: int):
         _cabi.check(self._lib.sqk_ctx_set_dtw_lanes(self._h, int(lanes)))
+
+    def set_dtw_plan(self, plan: str = "auto"):
+        """How exact (fp64) MotifSeq requests run: "single_pass" (float64 recurrence over every column),
+        "two_pass" (float32 lower-bound scan + float64 windows, same results bit for bit) or "auto"."""
+        _cabi.check(self._lib.sqk_ctx_set_dtw_plan(self._h, _cabi.DTW_PLAN[plan]))
+
+    def plan_counters(self) -> dict:
+        """Two-pass diagnostics of the most recent launch (first model): exact windows run, reads re-run in full."""
+        out = (C.c_int64 * 2)()
+        _cabi.check(self._lib.sqk_ctx_get_plan_counters(self._h, out))
+        return {"windows": int(out[0]), "fallback_reads": int(out[1])}
 
     def set_chunk_samples(self, samples: int):
         """Host mode: samples per in-flight chunk of the copy/compute pipeline (0 = default)."""

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "sqk_dtw_launch.cuh"
+#include "sqk_dtw_lb.cuh"
 #include "sqk_segmenter.cuh"
 #include "sqk_f64.cuh"
 #include "sqk_stats.cuh"
@@ -96,6 +97,7 @@ struct Pending { void *dst; const void *src; size_t bytes; };
 struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
+    DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -149,6 +151,7 @@ struct sqk_ctx {
     std::vector<cudaEvent_t> pool;
     sqk_timing acc{};
     int force_lanes = 0;
+    int dtw_plan = SQK_PLAN_AUTO;
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1;
 };
@@ -394,6 +397,26 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
     return SQK_OK;
 }
 
+static sqk_lb_launcher pick_lb(int L)
+{
+    switch (L) {
+    case 4: return sqk_launch_lb_l4;
+    case 8: return sqk_launch_lb_l8;
+    case 16: return sqk_launch_lb_l16;
+    default: return sqk_launch_lb_l32;
+    }
+}
+
+// Exact (float64) requests run as the two-pass plan when the reads are long enough for windows to pay:
+// the float32 lower-bound scan + float64 windows (sqk_dtw_plan.cuh).  Same results bit for bit.
+static bool want_two_pass(const sqk_ctx *c, const sqk_motif_params *p, int N, int64_t max_len)
+{
+    if (p->precision != SQK_PREC_FP64) return false;
+    if (c->dtw_plan == SQK_PLAN_SINGLE_PASS) return false;
+    if (c->dtw_plan == SQK_PLAN_TWO_PASS) return true;
+    return max_len >= 4ll * (sqk_lb_window(N) + N);
+}
+
 static int check_motif_params(const sqk_motif_params *p)
 {
     if (!p) return fail(SQK_ERR_ARG, "params is NULL");
@@ -402,22 +425,25 @@ static int check_motif_params(const sqk_motif_params *p)
     return SQK_OK;
 }
 
-// stats + one DTW launch per model over a device-resident View; d_hits is [n_reads][n_models]
+#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head
+
+// stats + the DTW of every model over a device-resident View; d_hits is [n_reads][n_models]
 static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
-                            const int32_t *h_model_offsets, int n_models, const sqk_motif_params *p, sqk_hit *d_hits,
-                            int32_t *d_nkept)
+                            const double *h_models, const int32_t *h_model_offsets, int n_models,
+                            const sqk_motif_params *p, sqk_hit *d_hits, int32_t *d_nkept)
 {
     if (v.n_reads == 0) return SQK_OK;
     if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
     TRY(launch_stats(c, s, st, v, p->scale_mode, p->lo, p->hi, 0, 0.0, d_nkept));
-    TRY(ensure(s.counter, 256 * sizeof(unsigned)));
     if (n_models > 256) return fail(SQK_ERR_UNSUPPORTED, "more than 256 models per call");
-    CU(cudaMemsetAsync(s.counter.p, 0, 256 * sizeof(unsigned), st));
+    TRY(ensure(s.counter, 256 * SQK_CTRS_PER_MODEL * sizeof(unsigned)));
+    CU(cudaMemsetAsync(s.counter.p, 0, (size_t)n_models * SQK_CTRS_PER_MODEL * sizeof(unsigned), st));
     for (int m = 0; m < n_models; m++) {
         const int N = h_model_offsets[m + 1] - h_model_offsets[m];
         int L = 0, K = 0;
         sqk_dtw_launcher fn = nullptr;
         TRY(pick_dtw(c, N, p->precision, &L, &K, &fn));
+        unsigned *ctr = (unsigned *)s.counter.p + (size_t)m * SQK_CTRS_PER_MODEL;
         DtwArgs a{};
         a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
         a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
@@ -425,11 +451,59 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.model = d_models + h_model_offsets[m]; a.N = N;
         a.lo = clamp_lim(p->lo); a.hi = clamp_lim(p->hi);
         a.hits = d_hits + m; a.hit_stride = n_models;
-        a.counter = (unsigned *)s.counter.p + m;
+        a.counter = ctr;
         cudaEvent_t eb;
-        TRY(tick(c, SQK_K_DTW, st, &eb));
-        cudaError_t e = fn(K, a, c->n_sms, st);
-        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        if (L < 4 || !want_two_pass(c, p, N, v.max_len)) {   // motifs of <= 4 points run one thread per read: single pass
+            TRY(tick(c, SQK_K_DTW, st, &eb));
+            cudaError_t e = fn(K, a, c->n_sms, st);
+            if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+            TRY(tock(eb, st));
+            continue;
+        }
+        // ---- two-pass plan: lower-bound scan -> exact windows -> finalize -> exact fallback ----------------
+        if ((int64_t)v.n_reads * SQK_LB_MAX_CLUSTERS > 0x7fffffffLL) return fail(SQK_ERR_ARG, "too many reads in one launch for the two-pass plan");
+        TRY(ensure(s.jobs, (size_t)v.n_reads * SQK_LB_MAX_CLUSTERS * sizeof(DtwJob)));
+        TRY(ensure(s.fbjobs, (size_t)v.n_reads * sizeof(DtwJob)));
+        TRY(ensure(s.lbreads, (size_t)v.n_reads * sizeof(LbRead)));
+        TRY(ensure(s.jobres, (size_t)v.n_reads * SQK_LB_MAX_CLUSTERS * sizeof(sqk_hit)));
+        double xmax = 0.0;
+        for (int i = h_model_offsets[m]; i < h_model_offsets[m + 1]; i++) xmax = std::max(xmax, std::fabs(h_models[i]));
+        if (!(xmax < 1e30)) return fail(SQK_ERR_ARG, "model %d holds a non-finite point", m);
+        LbArgs b{};
+        b.base = v.base; b.alloc_lo = v.alloc_lo; b.alloc_hi = v.alloc_hi;
+        b.offsets = v.offsets; b.read0 = v.read0; b.n_reads = (int)v.n_reads;
+        b.stats = a.stats; b.model = a.model; b.N = N; b.lo = a.lo; b.hi = a.hi;
+        b.hits = a.hits; b.hit_stride = a.hit_stride;
+        b.counter = ctr;
+        b.jobs = (DtwJob *)s.jobs.p; b.n_jobs = ctr + 1;
+        b.reads = (LbRead *)s.lbreads.p;
+        b.xmax_abs = xmax;
+        b.W = sqk_lb_window(N);
+        if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the fallback
+        b.short_len = 2 * (b.W + N);
+        TRY(tick(c, SQK_K_DTW_LB, st, &eb));
+        cudaError_t e = pick_lb(L)(K, b, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW lower-bound launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        TRY(tock(eb, st));
+
+        TRY(tick(c, SQK_K_DTW_WIN, st, &eb));
+        a.counter = ctr + 2;
+        a.jobs = b.jobs; a.n_jobs = ctr + 1;
+        a.job_out = (sqk_hit *)s.jobres.p; a.job_out_stride = 1;
+        e = fn(K, a, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW window launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        FinalizeArgs f{};
+        f.reads = b.reads; f.jobres = (const sqk_hit *)s.jobres.p; f.n_reads = (int)v.n_reads;
+        f.hits = a.hits; f.hit_stride = a.hit_stride;
+        f.base = v.base; f.offsets = v.offsets; f.read0 = v.read0; f.stats = a.stats;
+        f.fb_jobs = (DtwJob *)s.fbjobs.p; f.n_fb = ctr + 3;
+        sqk_dtw_finalize_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(f);
+        CU(cudaGetLastError());
+        a.counter = ctr + 4;
+        a.jobs = f.fb_jobs; a.n_jobs = ctr + 3;
+        a.job_out = a.hits; a.job_out_stride = a.hit_stride;
+        e = fn(K, a, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
         TRY(tock(eb, st));
     }
     return SQK_OK;
@@ -686,6 +760,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
         release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes);
+        release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -759,6 +834,29 @@ int sqk_ctx_set_chunk_samples(sqk_ctx *c, int64_t samples)
     return SQK_OK;
 }
 
+int sqk_ctx_set_dtw_plan(sqk_ctx *c, int plan)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (plan != SQK_PLAN_AUTO && plan != SQK_PLAN_SINGLE_PASS && plan != SQK_PLAN_TWO_PASS)
+        return fail(SQK_ERR_ARG, "plan must be SQK_PLAN_AUTO, SQK_PLAN_SINGLE_PASS or SQK_PLAN_TWO_PASS");
+    c->dtw_plan = plan;
+    return SQK_OK;
+}
+
+int sqk_ctx_get_plan_counters(sqk_ctx *c, int64_t out[2])
+{
+    if (!c || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    Guard g(c->device);
+    out[0] = out[1] = 0;
+    if (!c->slot[0].counter.p) return SQK_OK;
+    CU(cudaStreamSynchronize(device_stream(c)));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    unsigned h[SQK_CTRS_PER_MODEL];
+    CU(cudaMemcpy(h, c->slot[0].counter.p, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[1]; out[1] = h[3];
+    return SQK_OK;
+}
+
 int sqk_ctx_set_dtw_lanes(sqk_ctx *c, int lanes)
 {
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
@@ -796,7 +894,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
         // device mode: the caller's allocation bounds are unknown, so [offsets[0], offsets[n]) delimits what the
         // kernels may touch (resolve_bounds): 16-byte blocks sticking out of it are read sample by sample.
-        TRY(enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, model_offsets, n_models, p, hits, n_kept));
+        TRY(enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, models, model_offsets, n_models, p, hits, n_kept));
         return SQK_OK;
     }
 
@@ -827,7 +925,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
         if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
-        TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
+        TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, models, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
                              (int32_t *)s.nkept.p));
         TRY(result_to_host(s, 0, hits + r0 * n_models, s.hits.p, (size_t)nr * n_models * sizeof(sqk_hit), hits_pinned));
         if (n_kept) TRY(result_to_host(s, 1, n_kept + r0, s.nkept.p, (size_t)nr * sizeof(int32_t), nkept_pinned));
@@ -1050,7 +1148,7 @@ int sqk_motifseq_trace(sqk_ctx *c, const int16_t *signal, int64_t n_samples, con
     CU(cudaMemcpyAsync(c->model.p, model, (size_t)n_model * sizeof(double), cudaMemcpyHostToDevice, st));
     View v{(const int16_t *)s.signals.p, 0, n_samples, (const int64_t *)s.offsets.p, 0, 1, n_samples};
     const int32_t mo[2] = {0, n_model};
-    TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, mo, 1, p, (sqk_hit *)s.hits.p, (int32_t *)s.nkept.p));
+    TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, model, mo, 1, p, (sqk_hit *)s.hits.p, (int32_t *)s.nkept.p));
     ReadStats rs;
     sqk_hit h;
     CU(cudaMemcpyAsync(&rs, s.stats.p, sizeof(rs), cudaMemcpyDeviceToHost, st));

@@ -24,8 +24,15 @@
 // shared memory holding 16*L doubles; the DTW consumes one ring entry per step.  Groups pull
 // reads from a global atomic counter and re-arm independently, so ragged read lengths need no
 // sorting and the tail is one read per group.
+//
+// JOBS variant (pass 2 of the exact two-pass plan, sqk_dtw_plan.cuh).  The work items are DtwJob records --
+// a column window of a read, or a whole read -- instead of reads.  A tainted job treats its first column as a
+// boundary: after computing it, rows >= 1 are overwritten with cost -1 and the pointer SQK_TAINT, a strict lower
+// bound of whatever the columns in front of the window would have delivered.  The last-row argmin only looks at
+// columns >= arg_lo (the candidate cluster); if the minimum carries the taint the job reports start = SQK_TAINT.
 #pragma once
 #include "sqk_common.cuh"
+#include "sqk_dtw_plan.cuh"
 
 #define SQK_DTW_WARPS 4
 #define SQK_DTW_THREADS (SQK_DTW_WARPS * 32)
@@ -49,6 +56,11 @@ struct DtwArgs {
     int hit_stride;
     unsigned int *counter;    // work queue head, zeroed before launch
     const double *prenorm;    // float64 front end: prenorm[offsets[r] + i] = i-th normalised kept sample (else null)
+    // JOBS variant only
+    const DtwJob *jobs;       // work items
+    const unsigned int *n_jobs;   // how many (device memory: produced by the previous kernel)
+    sqk_hit *job_out;         // job_out[job.out * job_out_stride]
+    int job_out_stride;
 };
 
 template <typename T> struct DtwNum;
@@ -66,11 +78,11 @@ template <> struct DtwNum<float> {
 
 // One wavefront step of one lane: column (t - l) for this lane's K rows.  (ci, si) hold the previous
 // column of these rows, (co, so) receive the new one.
-template <typename T, int K, int L, bool RAGGED>
+template <typename T, int K, int L, bool RAGGED, bool JOBS>
 __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T (&co)[K], int (&so)[K],
                                          const T (&x)[K], const T *ring, int l, bool pass0, int t, int n_last,
                                          T &bot_c, int &bot_s, T &prev_up_c, int &prev_up_s,
-                                         T &best, int &best_j, int &best_s)
+                                         T &best, int &best_j, int &best_s, int arg_lo, bool tainted)
 {
     using Num = DtwNum<T>;
     constexpr int RC = 16 * L;
@@ -95,17 +107,28 @@ __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T
         co[k] = nc; so[k] = m_s;
     }
     bot_c = u_c; bot_s = u_s;
+    if constexpr (JOBS) {
+        if (tainted && t == l) {
+            // this lane just computed the window's boundary column: rows >= 1 become the strict lower bound -1 with
+            // the taint pointer (row 0 keeps its exact value |x_0 - y|: it has no left neighbour in mlpy's recurrence)
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (k > 0 || l > 0) { co[k] = (T)-1; so[k] = SQK_TAINT; }
+            if (K > 1 || l > 0) { bot_c = (T)-1; bot_s = SQK_TAINT; }
+        }
+    }
     // running first-argmin of the last row: n_last is the read length in lane L-1 and 0 elsewhere, so only
     // the lane that owns the last motif row can fire.  New minima are rare (O(log M) per read), so the update
     // sits behind a warp vote instead of costing four selects every step.
     const int j = t - (L - 1);
-    const bool better = (unsigned)j < (unsigned)n_last && bot_c < best;
+    // n_last counts the columns from arg_lo on (JOBS) / from 0 on
+    const bool better = (unsigned)(JOBS ? j - arg_lo : j) < (unsigned)n_last && bot_c < best;
     if (__any_sync(SQK_FULL_MASK, better)) {
         if (better) { best = bot_c; best_j = j; best_s = bot_s; }
     }
 }
 
-template <typename T, int K, int L, bool RAGGED>
+template <typename T, int K, int L, bool RAGGED, bool JOBS = false>
 __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kernel(const DtwArgs a)
 {
     constexpr int G = 32 / L;          // reads per warp
@@ -118,6 +141,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
 
     int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
     resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
+    const unsigned n_items = JOBS ? *a.n_jobs : (unsigned)a.n_reads;
 
     const int lane = threadIdx.x & 31;
     const int l = lane % L;            // lane within the group
@@ -142,6 +166,8 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
     T bot_c = Num::inf(), prev_up_c = Num::inf(), best = Num::inf();
     int bot_s = 0, prev_up_s = 0, best_j = -1, best_s = -1;
     int n = 0, n_last = 0, t = 0, wcount = 0, my_read = -1;
+    int col0 = 0, arg_lo = 0;          // JOBS: first column of the window, first column the argmin looks at
+    bool tainted = false;
     int64_t begin = 0, end = 0, cursor = 0;
     double center = 0.0, scale = 1.0;
     bool done = true, exhausted = false;
@@ -158,8 +184,28 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
             if (done && !exhausted) {
                 const unsigned below = need & ((1u << (g * L)) - 1u);
                 const unsigned idx = head + __popc(below);
-                if (idx >= (unsigned)a.n_reads) {
+                if (idx >= n_items) {
                     exhausted = true;
+                } else if constexpr (JOBS) {
+                    const DtwJob jb = a.jobs[idx];
+                    my_read = jb.out;
+                    const int64_t r = a.read0 + jb.read;
+                    begin = a.offsets[r];
+                    end = a.offsets[r + 1];
+                    const ReadStats st = a.stats[jb.read];
+                    center = st.center; scale = st.scale;
+                    n = jb.n_cols; col0 = jb.col0; arg_lo = jb.arg_lo; tainted = jb.tainted != 0;
+                    if (n > arg_lo && arg_lo >= 0) {       // always true for jobs built by pass 1 / finalize
+                        done = false;
+                        n_last = (l == L - 1) ? n - arg_lo : 0;
+                        t = 0; wcount = 0;
+                        cursor = jb.cursor;
+#pragma unroll
+                        for (int k = 0; k < K; k++) { c[k] = Num::inf(); s[k] = 0; }
+                        bot_c = Num::inf(); bot_s = 0;
+                        prev_up_c = (l == 0) ? (T)0 : Num::inf(); prev_up_s = 0;
+                        best = Num::inf(); best_j = -1; best_s = -1;
+                    }
                 } else {
                     my_read = (int)idx;
                     const int64_t r = a.read0 + idx;
@@ -194,7 +240,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
         if (__all_sync(SQK_FULL_MASK, exhausted)) break;   // exhausted implies done; others re-pull above
 
         // ---- refill the rings: raw int16 -> filter -> normalise -> shared memory ---------------
-        if (a.prenorm != nullptr) {
+        if (!JOBS && a.prenorm != nullptr) {
             // float64 front end (sqk_f64.cuh): the read is already compacted and normalised in a global row
             for (;;) {
                 const bool want = !done && (wcount < t + S) && (wcount < n);
@@ -252,9 +298,9 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
         //      so no register-to-register copies are needed to keep the previous column alive) ----
 #pragma unroll 1
         for (int it = 0; it < S; it += 2) {
-            dtw_step<T, K, L, RAGGED>(c, s, c2, s2, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+            dtw_step<T, K, L, RAGGED, JOBS>(c, s, c2, s2, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted);
             t++;
-            dtw_step<T, K, L, RAGGED>(c2, s2, c, s, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+            dtw_step<T, K, L, RAGGED, JOBS>(c2, s2, c, s, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted);
             t++;
         }
         __syncwarp();
@@ -262,7 +308,13 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
         if (!done && t >= n + L - 1) {
             if (l == L - 1) {
                 sqk_hit h; h.start = best_s; h.end = best_j; h.dist = (double)best;
-                a.hits[(int64_t)my_read * a.hit_stride] = h;
+                if constexpr (JOBS) {
+                    h.start = best_s == SQK_TAINT ? SQK_TAINT : col0 + best_s;   // window columns -> read columns
+                    h.end = col0 + best_j;
+                    a.job_out[(int64_t)my_read * a.job_out_stride] = h;
+                } else {
+                    a.hits[(int64_t)my_read * a.hit_stride] = h;
+                }
             }
             done = true;
         }

@@ -1,0 +1,289 @@
+// sqk_dtw_lb.cuh -- pass 1 of the exact two-pass plan (sqk_dtw_plan.cuh): a float32, cost-only, rounded-down
+// lower bound of the last row of mlpy's subsequence-DTW cost matrix (MotifSeq.py:437), fused with the same
+// int16 -> outlier filter -> normalise front end as the exact kernel.  4 instructions per cell
+// (FADD.RZ, FADD.RM, FMNMX3, FADD.RM) instead of ~12; no start pointers, no float64 in the recurrence.
+//
+// Same mapping as sqk_dtw_kernel: L lanes per read, K motif rows per lane in registers, skewed wavefront,
+// one __shfl_up per step, normalised samples staged in a per-group shared-memory ring.  The lane that owns the
+// last motif row watches L[j] against the candidate threshold (vote-gated, candidates are rare) and keeps the
+// candidate clusters; refill checkpoints (kept-sample count in front of every refill) let it translate a
+// cluster into the raw position its exact window starts at.  At the end of a read it appends one DtwJob per
+// cluster to the job list consumed by sqk_dtw_kernel<JOBS>.
+#pragma once
+#include "sqk_common.cuh"
+#include "sqk_dtw_plan.cuh"
+
+#define SQK_LB_WARPS 4
+#define SQK_LB_THREADS (SQK_LB_WARPS * 32)
+#define SQK_LB_MINB(K) ((K) <= 10 ? 6 : ((K) <= 16 ? 5 : ((K) <= 20 ? 4 : 2)))
+
+struct LbArgs {
+    const int16_t *base;      // base[i] = absolute sample i
+    int64_t alloc_lo, alloc_hi;
+    const int64_t *offsets;   // absolute
+    int64_t read0;
+    int n_reads;
+    const ReadStats *stats;   // [n_reads]
+    const double *model;      // N motif points
+    int N;
+    int lo, hi;
+    sqk_hit *hits;            // hits[i * hit_stride]: only written for empty / degenerate reads
+    int hit_stride;
+    unsigned int *counter;    // work queue head, zeroed before launch
+    DtwJob *jobs;             // job list (capacity n_reads * SQK_LB_MAX_CLUSTERS)
+    unsigned int *n_jobs;     // its length, zeroed before launch
+    LbRead *reads;            // [n_reads]
+    double xmax_abs;          // max |motif point|
+    int W;                    // window columns in front of a cluster
+    int short_len;            // reads with n_kept <= short_len skip pass 1 (one full-length job)
+};
+
+template <int K, int L, bool RAGGED>
+__device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], const float (&x)[K], const float *ring, int l,
+                                        bool pass0, int t, int n_last, float w, float &bot, float &prev_up,
+                                        float &runmin, float &thr, float aeps, float bslack, LbClusters *cl,
+                                        const int32_t *ck, int n_ref, int64_t cursor0, int W)
+{
+    constexpr int RC = 16 * L;
+    float up = __shfl_up_sync(SQK_FULL_MASK, bot, 1, L);
+    if (l == 0) up = 0.0f;                             // virtual row above row 0: free start
+    const float y = ring[(t - l) & (RC - 1)];
+    float dg = prev_up;
+    prev_up = up;
+    float u = up;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float lf = ci[k];
+        const float m = fminf(fminf(u, dg), lf);
+        float nc = sqk_add_rd(sqk_lb_local(x[k], y, w), m);
+        if (RAGGED && k == 0 && pass0) nc = up;        // pass-through slot (only when L*K != N)
+        dg = lf;
+        u = nc;
+        co[k] = nc;
+    }
+    bot = u;
+    const int j = t - (L - 1);
+    const bool ev = (unsigned)j < (unsigned)n_last && bot <= thr;
+    if (__any_sync(SQK_FULL_MASK, ev)) {
+        if (ev) {
+            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = 8 * L; sc.W = W;
+            lbc_event(*cl, j, bot, runmin, thr, aeps, bslack, sc);
+        }
+    }
+}
+
+template <int K, int L, bool RAGGED>
+__global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_kernel(const LbArgs a)
+{
+    constexpr int G = 32 / L;          // reads per warp
+    constexpr int RC = 16 * L;         // ring capacity (entries), power of two
+    constexpr int S = (L == 1) ? 8 : 7 * L;   // steps between ring refills
+    constexpr int CH = 8 * L;          // raw samples fetched per refill
+
+    __shared__ float ring_all[SQK_LB_WARPS * G * RC];
+    __shared__ int32_t ck_all[SQK_LB_WARPS * G * SQK_LB_CKPT];
+    __shared__ LbClusters cl_all[SQK_LB_WARPS * G];
+
+    int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
+    resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
+
+    const int lane = threadIdx.x & 31;
+    const int l = lane % L;
+    const int g = lane / L;
+    const int gid = (threadIdx.x >> 5) * G + g;
+    float *ring = ring_all + gid * RC;
+    int32_t *ck = ck_all + gid * SQK_LB_CKPT;
+    LbClusters *cl = cl_all + gid;
+    for (int q = l; q < RC; q += L) ring[q] = 0.0f;
+    __syncwarp();
+
+    const int P = L * K - a.N;
+    const bool pass0 = (l >= L - P);
+    const int row0 = pass0 ? (L - P) * K + (l - (L - P)) * (K - 1) - 1 : l * K;
+    float x[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int row = row0 + k;
+        x[k] = (row >= 0 && row < a.N) ? (float)a.model[row] : 0.0f;
+    }
+
+    const float inf = __int_as_float(0x7f800000);
+    float c[K], c2[K];
+    float bot = inf, prev_up = inf, runmin = inf, thr = inf, w = 0.0f, aeps = 0.0f, bslack = 0.0f;
+    int n = 0, n_last = 0, t = 0, wcount = 0, my_read = -1, n_ref = 0;
+    int64_t begin = 0, end = 0, cursor = 0, cursor0 = 0;
+    double center = 0.0, scale = 1.0;
+    bool done = true, exhausted = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) c[k] = inf;
+
+    for (;;) {
+        // ---- groups that finished pull the next read -------------------------------------------
+        const unsigned need = __ballot_sync(SQK_FULL_MASK, done && !exhausted && l == 0);
+        if (need) {
+            unsigned head = 0;
+            if (lane == 0) head = atomicAdd(a.counter, (unsigned)__popc(need));
+            head = __shfl_sync(SQK_FULL_MASK, head, 0);
+            if (done && !exhausted) {
+                const unsigned below = need & ((1u << (g * L)) - 1u);
+                const unsigned idx = head + __popc(below);
+                if (idx >= (unsigned)a.n_reads) {
+                    exhausted = true;
+                } else {
+                    my_read = (int)idx;
+                    const int64_t r = a.read0 + idx;
+                    begin = a.offsets[r];
+                    end = a.offsets[r + 1];
+                    const ReadStats st = a.stats[idx];
+                    n = st.n_kept;
+                    center = st.center; scale = st.scale;
+                    if (st.flags & SQK_FLAG_DEGENERATE) n = -1;
+                    if (st.flags & SQK_FLAG_TOO_LONG) n = -2;
+                    cursor0 = aligned_block_start(a.base, begin);
+                    if (n <= 0) {
+                        // same status records as sqk_dtw_kernel: -1 empty, -2 scale undefined, -3 longer than declared
+                        if (l == L - 1) {
+                            sqk_hit h; h.start = n == 0 ? -1 : (n == -1 ? -2 : -3); h.end = h.start; h.dist = __longlong_as_double(0x7ff8000000000000LL);
+                            a.hits[(int64_t)idx * a.hit_stride] = h;
+                            LbRead rec; rec.min_l = 0.0f; rec.thr = 0.0f; rec.n_jobs = -1; rec.flags = 0;
+                            a.reads[idx] = rec;
+                        }
+                    } else if (n <= a.short_len || n > SQK_LB_MAX_LEN) {
+                        // too short for a window to save anything (or beyond what the proof covers): the exact kernel
+                        // takes the whole read as one job
+                        if (l == L - 1) {
+                            DtwJob jb; jb.cursor = cursor0; jb.read = (int)idx; jb.col0 = 0; jb.n_cols = n; jb.arg_lo = 0;
+                            jb.tainted = 0; jb.out = (int)idx * SQK_LB_MAX_CLUSTERS;
+                            a.jobs[atomicAdd(a.n_jobs, 1u)] = jb;
+                            LbRead rec; rec.min_l = 0.0f; rec.thr = inf; rec.n_jobs = 1; rec.flags = 0;
+                            a.reads[idx] = rec;
+                        }
+                    } else {
+                        done = false;
+                        n_last = (l == L - 1) ? n : 0;
+                        t = 0; wcount = 0; n_ref = 0;
+                        cursor = cursor0;
+#pragma unroll
+                        for (int k = 0; k < K; k++) c[k] = inf;
+                        bot = inf;
+                        prev_up = (l == 0) ? 0.0f : inf;
+                        runmin = inf; thr = inf;
+                        w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
+                        sqk_lb_slack(a.N, w, &aeps, &bslack);
+                        if (l == L - 1) lbc_reset(*cl);
+                    }
+                }
+            }
+        }
+        if (__all_sync(SQK_FULL_MASK, exhausted)) break;
+
+        // ---- refill the rings: raw int16 -> filter -> normalise -> float32 -> shared memory ------
+        for (;;) {
+            const bool want = !done && (wcount < t + S) && (cursor < end);
+            if (!__any_sync(SQK_FULL_MASK, want)) break;
+            unsigned keep = 0;
+            Samples8 smp;
+            const int64_t blk = cursor + l * 8;
+            if (want && blk < end) {
+                smp = load_block8(a.base, blk, alloc_lo, alloc_hi);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int v = smp.get(e);
+                    const int64_t idx = blk + e;
+                    if (idx >= begin && idx < end && v > a.lo && v < a.hi) keep |= 1u << e;
+                }
+            }
+            const int cnt = __popc(keep);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < L; d <<= 1) {
+                const int u = __shfl_up_sync(SQK_FULL_MASK, incl, d, L);
+                if (l >= d) incl += u;
+            }
+            const int group_total = __shfl_sync(SQK_FULL_MASK, incl, L - 1, L);
+            if (keep) {
+                int pos = wcount + incl - cnt;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (keep & (1u << e)) {
+                        const double y = __ddiv_rn(__dsub_rn((double)smp.get(e), center), scale);
+                        ring[pos & (RC - 1)] = (float)y;      // round to nearest: |y - y32| <= 2^-24 |y|
+                        pos++;
+                    }
+                }
+            }
+            if (want) {
+                if (l == 0) ck[n_ref % SQK_LB_CKPT] = wcount;   // kept samples in front of refill n_ref
+                n_ref++;
+                wcount += group_total; cursor += CH;
+            }
+        }
+        __syncwarp();
+
+#pragma unroll 1
+        for (int it = 0; it < S; it += 2) {
+            lb_step<K, L, RAGGED>(c, c2, x, ring, l, pass0, t, n_last, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, n_ref, cursor0, a.W);
+            t++;
+            lb_step<K, L, RAGGED>(c2, c, x, ring, l, pass0, t, n_last, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, n_ref, cursor0, a.W);
+            t++;
+        }
+        __syncwarp();
+
+        if (!done && t >= n + L - 1) {
+            if (l == L - 1) {
+                lbc_finish(*cl, thr);
+                LbRead rec; rec.min_l = runmin; rec.thr = thr; rec.n_jobs = 0; rec.flags = cl->overflow;
+                if (cl->n == 0) rec.flags |= 2;           // cannot happen (the minimum itself is a candidate); be safe
+                for (int q = 0; q < cl->n; q++)
+                    if (cl->tainted[q] < 0) rec.flags |= 4;   // its boundary column had already left the checkpoint ring
+                if (rec.flags == 0) {
+                    const int nj = cl->n;
+                    const unsigned at = atomicAdd(a.n_jobs, (unsigned)nj);
+                    for (int q = 0; q < nj; q++) {
+                        DtwJob jb;
+                        jb.cursor = cl->cursor[q]; jb.read = my_read; jb.col0 = cl->col0[q]; jb.n_cols = cl->hi[q] - cl->col0[q] + 1;
+                        jb.arg_lo = cl->lo[q] - cl->col0[q]; jb.tainted = cl->tainted[q]; jb.out = my_read * SQK_LB_MAX_CLUSTERS + q;
+                        a.jobs[at + q] = jb;
+                    }
+                    rec.n_jobs = nj;
+                }
+                a.reads[my_read] = rec;
+            }
+            done = true;
+        }
+    }
+}
+
+// Combine the window results of every read; reads that are not proven get a full-length job in the fallback list.
+struct FinalizeArgs {
+    const LbRead *reads;
+    const sqk_hit *jobres;     // [n_reads][SQK_LB_MAX_CLUSTERS]
+    int n_reads;
+    sqk_hit *hits; int hit_stride;
+    const int16_t *base; const int64_t *offsets; int64_t read0;
+    const ReadStats *stats;
+    DtwJob *fb_jobs; unsigned int *n_fb;
+};
+
+static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const LbRead rec = a.reads[r];
+    if (rec.n_jobs < 0) return;                        // status hit already written by pass 1
+    SqkHitLite res[SQK_LB_MAX_CLUSTERS], best;
+    const int nj = rec.n_jobs < SQK_LB_MAX_CLUSTERS ? rec.n_jobs : SQK_LB_MAX_CLUSTERS;
+    for (int q = 0; q < nj; q++) {
+        const sqk_hit h = a.jobres[(int64_t)r * SQK_LB_MAX_CLUSTERS + q];
+        res[q].start = h.start; res[q].end = h.end; res[q].dist = h.dist;
+    }
+    if (sqk_lb_decide(rec, res, &best)) {
+        sqk_hit h; h.start = best.start; h.end = best.end; h.dist = best.dist;
+        a.hits[(int64_t)r * a.hit_stride] = h;
+    } else {
+        DtwJob jb;
+        jb.cursor = aligned_block_start(a.base, a.offsets[a.read0 + r]);
+        jb.read = r; jb.col0 = 0; jb.n_cols = a.stats[r].n_kept; jb.arg_lo = 0; jb.tainted = 0; jb.out = r;
+        a.fb_jobs[atomicAdd(a.n_fb, 1u)] = jb;
+    }
+}

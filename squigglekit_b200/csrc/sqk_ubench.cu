@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "sqk_dtw_experiments.cuh"
+#include "sqk_dtw_lb.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
@@ -32,8 +33,8 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) ub_dtw(int steps, const doubl
     int bot_s = 0, prev_up_s = 0, best_j = -1, best_s = -1;
     const int n = (l == L - 1) ? steps : 0;
     for (int t = 0; t < steps; t += 2) {
-        dtw_step<T, K, L, false>(c, s, c2, s2, x, ring, l, false, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
-        dtw_step<T, K, L, false>(c2, s2, c, s, x, ring, l, false, t + 1, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s);
+        dtw_step<T, K, L, false, false>(c, s, c2, s2, x, ring, l, false, t, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, 0, false);
+        dtw_step<T, K, L, false, false>(c2, s2, c, s, x, ring, l, false, t + 1, n, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, 0, false);
     }
     T acc = best + (T)best_j + (T)best_s;
 #pragma unroll
@@ -88,6 +89,66 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS) ub_dtw2(int steps, const doub
 #pragma unroll
     for (int k = 0; k < K; k++) acc += c[k] + (T)s[k];
     if (acc == (T)123456.789) sink[0] = acc;
+}
+
+// the inner step of the float32 lower-bound kernel (pass 1 of the two-pass plan), register/shared-memory only
+template <int K, int L>
+__global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb(int steps, const double *model, float *sink)
+{
+    constexpr int G = 32 / L, RC = 16 * L;
+    __shared__ float ring_all[SQK_LB_WARPS * G * RC];
+    __shared__ LbClusters cl_all[SQK_LB_WARPS * G];
+    __shared__ int32_t ck_all[SQK_LB_WARPS * G * SQK_LB_CKPT];
+    const int lane = threadIdx.x & 31, l = lane % L, g = lane / L;
+    const int gid = (threadIdx.x >> 5) * G + g;
+    float *ring = ring_all + gid * RC;
+    LbClusters *cl = cl_all + gid;
+    int32_t *ck = ck_all + gid * SQK_LB_CKPT;
+    for (int q = l; q < SQK_LB_CKPT; q += L) ck[q] = q * 60;
+    for (int q = l; q < RC; q += L) ring[q] = (float)(((q * 2654435761u) >> 20) & 1023) * (1.0f / 256) - 2.0f;
+    if (l == L - 1) lbc_reset(*cl);
+    __syncwarp();
+    float x[K], c[K], c2[K];
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < K; k++) { x[k] = (float)model[(l * K + k) % 80]; c[k] = inf; }
+    float bot = inf, prev_up = (l == 0) ? 0.0f : inf, runmin = inf, thr = inf, aeps = 0.0f, bslack = 0.0f;
+    const float w = sqk_lb_width(2.0, 8.0);
+    sqk_lb_slack(80, w, &aeps, &bslack);
+    const int n = (l == L - 1) ? steps : 0;
+    for (int t = 0; t < steps; t += 2) {
+        lb_step<K, L, false>(c, c2, x, ring, l, false, t, n, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, t / 64, 0, 192);
+        lb_step<K, L, false>(c2, c, x, ring, l, false, t + 1, n, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, t / 64, 0, 192);
+    }
+    float acc = runmin + thr + (float)cl->n;
+#pragma unroll
+    for (int k = 0; k < K; k++) acc += c[k];
+    if (acc == 123456.789f) sink[0] = acc;
+}
+
+template <int K, int L>
+static void run_lb(int sms, const double *d_model, void *d_sink)
+{
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ub_lb<K, L>, SQK_LB_THREADS, 0));
+    const int grid = sms * occ, steps = 8192;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    ub_lb<K, L><<<grid, SQK_LB_THREADS>>>(256, d_model, (float *)d_sink);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(a));
+        ub_lb<K, L><<<grid, SQK_LB_THREADS>>>(steps, d_model, (float *)d_sink);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double cells = (double)grid * SQK_LB_THREADS * K * steps;
+    printf("{\"bench\": \"lb_step\", \"precision\": \"fp32_rd\", \"K\": %d, \"L\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, "
+           "\"cells_per_s\": %.4e}\n", K, L, occ, best_ms, cells / (best_ms * 1e-3));
+    fflush(stdout);
 }
 
 template <typename T, int K, int L>
@@ -233,6 +294,9 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&d_sink, 64));
     CK(cudaMemcpy(d_model, model.data(), 80 * sizeof(double), cudaMemcpyHostToDevice));
     printf("{\"bench\": \"device\", \"sms\": %d, \"clock_khz\": %d}\n", sms, clk);
+    run_lb<10, 8>(sms, d_model, d_sink);
+    run_lb<20, 4>(sms, d_model, d_sink);
+    run_lb<5, 16>(sms, d_model, d_sink);
     run_dtw<double, 20, 4>("fp64", sms, d_model, d_sink);
     run_dtw<double, 10, 8>("fp64", sms, d_model, d_sink);
     run_dtw<double, 5, 16>("fp64", sms, d_model, d_sink);

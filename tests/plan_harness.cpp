@@ -1,0 +1,152 @@
+// plan_harness.cpp -- CPU replay of the exact two-pass DTW plan (squigglekit_b200/csrc/sqk_dtw_plan.cuh).
+// Test infrastructure: compiled with g++ by tests/test_plan_cpu.py; it includes the SAME header the CUDA kernels
+// use, so the candidate threshold, the cluster bookkeeping, the window-start search, the taint rule and the
+// final decision are exercised here bit for bit (float32 directed rounding is emulated in the header's host
+// branch).  The recurrences themselves are plain scalar loops written after mlpy's C loop.
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../squigglekit_b200/csrc/sqk_dtw_plan.cuh"
+
+namespace {
+
+struct Hit { int start, end; double dist; };
+
+// exact float64 recurrence with forward start pointers on columns [col0, col0 + n_cols) of y; argmin over
+// columns >= col0 + arg_lo; tainted: column col0 is a boundary (rows >= 1 := -1 / SQK_TAINT).
+Hit exact_window(const double *x, int N, const double *y, int col0, int n_cols, int arg_lo, bool tainted,
+                 std::vector<double> *last_row = nullptr)
+{
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<double> c(N, inf), nc(N);
+    std::vector<int> s(N, 0), ns(N);
+    Hit best{-1, -1, inf};
+    for (int jj = 0; jj < n_cols; jj++) {
+        const double yj = y[col0 + jj];
+        for (int i = 0; i < N; i++) {
+            double m; int ms;
+            if (i == 0) { m = 0.0; ms = jj; }
+            else {
+                // diagonal if it ties the minimum, else left, else up (mlpy's back-trace preference)
+                const double dg = jj == 0 ? inf : c[i - 1], lf = jj == 0 ? inf : c[i], up = nc[i - 1];
+                const int dgs = jj == 0 ? 0 : s[i - 1], lfs = jj == 0 ? 0 : s[i], ups = ns[i - 1];
+                m = dg; ms = dgs;
+                if (lf < m) { m = lf; ms = lfs; }
+                if (up < m) { m = up; ms = ups; }
+            }
+            nc[i] = std::fabs(x[i] - yj) + m;
+            ns[i] = ms;
+        }
+        if (tainted && jj == 0)
+            for (int i = 1; i < N; i++) { nc[i] = -1.0; ns[i] = SQK_TAINT; }
+        c.swap(nc); s.swap(ns);
+        if (last_row) (*last_row)[jj] = c[N - 1];
+        if (jj >= arg_lo && c[N - 1] < best.dist) { best.dist = c[N - 1]; best.end = jj; best.start = s[N - 1]; }
+    }
+    if (best.start != SQK_TAINT) best.start += col0;
+    best.end += col0;
+    return best;
+}
+
+}  // namespace
+
+extern "C" {
+
+// y: normalised kept samples (float64) of one read, n of them; keep[raw_len]: 1 where the raw sample survived the
+// outlier filter (sum == n); align_off: raw samples between the aligned block start and the read's first sample;
+// ch: raw samples per refill (8 * lanes).  out: start, end; *dist.  diag[0..7]: n_clusters, n_jobs, fallback
+// (0 proven, 1 fallback), flags, lower-bound violations (must be 0), tainted windows, window columns, max L gap *1e9.
+int plan_two_pass(const double *x, int N, const double *y, int n, const uint8_t *keep, int raw_len, int align_off, int ch,
+                  int lo, int hi, double center, double scale, int W, int32_t *out, double *dist, int64_t *diag)
+{
+    const float inf = std::numeric_limits<float>::infinity();
+    double xmax = 0.0;
+    for (int i = 0; i < N; i++) xmax = std::fmax(xmax, std::fabs(x[i]));
+    const float w = sqk_lb_width(xmax, sqk_lb_ymax(lo, hi, center, scale));
+    float aeps, bslack;
+    sqk_lb_slack(N, w, &aeps, &bslack);
+    if (W <= 0) W = sqk_lb_window(N);
+
+    // exact last row of the whole read: the property under test is L[j] <= C[N-1][j]
+    std::vector<double> crow(n);
+    const Hit truth = exact_window(x, N, y, 0, n, 0, false, &crow);
+
+    // ---- pass 1: float32 lower bound, candidate clusters, refill checkpoints ------------------------------
+    std::vector<float> x32(N), c(N, inf), nc(N);
+    for (int i = 0; i < N; i++) x32[i] = (float)x[i];
+    LbClusters cl; lbc_reset(cl);
+    float runmin = inf, thr = inf;
+    int32_t ck[SQK_LB_CKPT];
+    int n_ref = 0, wcount = 0, raw = -align_off;       // raw: position of the next refill relative to the read's first sample
+    int64_t violations = 0; double max_gap = 0.0;
+    for (int j = 0; j < n; j++) {
+        // the kernel refills ahead of use (whenever fewer than S columns are buffered beyond the wavefront)
+        const int lanes = ch / 8, S = lanes == 1 ? 8 : 7 * lanes;
+        while (wcount < j + lanes + S && raw < raw_len) {
+            ck[n_ref % SQK_LB_CKPT] = wcount; n_ref++;
+            for (int e = 0; e < ch; e++) { const int r = raw + e; if (r >= 0 && r < raw_len && keep[r]) wcount++; }
+            raw += ch;
+        }
+        const float y32 = (float)y[j];
+        for (int i = 0; i < N; i++) {
+            float m;
+            if (i == 0) m = 0.0f;
+            else {
+                const float dg = j == 0 ? inf : c[i - 1], lf = j == 0 ? inf : c[i], up = nc[i - 1];
+                m = std::fmin(std::fmin(up, dg), lf);
+            }
+            nc[i] = sqk_add_rd(sqk_lb_local(x32[i], y32, w), m);
+        }
+        c.swap(nc);
+        const float v = c[N - 1];
+        if (!((double)v <= crow[j])) violations++;
+        if (crow[j] - (double)v > max_gap && crow[j] <= truth.dist + 1.0) max_gap = crow[j] - (double)v;
+        if (v <= thr) {
+            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = -(int64_t)align_off; sc.ch = ch; sc.W = W;
+            lbc_event(cl, j, v, runmin, thr, aeps, bslack, sc);
+        }
+    }
+    lbc_finish(cl, thr);
+    LbRead rec; rec.min_l = runmin; rec.thr = thr; rec.n_jobs = 0; rec.flags = cl.overflow;
+    if (cl.n == 0) rec.flags |= 2;
+    for (int q = 0; q < cl.n; q++)
+        if (cl.tainted[q] < 0) rec.flags |= 4;
+    if (rec.flags == 0) rec.n_jobs = cl.n;
+
+    // ---- pass 2: exact windows --------------------------------------------------------------------------
+    SqkHitLite res[SQK_LB_MAX_CLUSTERS], best;
+    int64_t tainted_windows = 0, window_cols = 0;
+    for (int q = 0; q < rec.n_jobs; q++) {
+        // the window starts at the first kept sample at/after raw position cursor: that must be column col0
+        int kept_before = 0;
+        for (int r = 0; r < cl.cursor[q] && r < raw_len; r++) kept_before += keep[r];
+        if (kept_before != cl.col0[q]) return -100 - q;                 // checkpoint bookkeeping broken
+        const int n_cols = cl.hi[q] - cl.col0[q] + 1;
+        const Hit h = exact_window(x, N, y, cl.col0[q], n_cols, cl.lo[q] - cl.col0[q], cl.tainted[q] != 0);
+        res[q].start = h.start; res[q].end = h.end; res[q].dist = h.dist;
+        if (h.start == SQK_TAINT) tainted_windows++;
+        window_cols += n_cols;
+    }
+    const bool proven = sqk_lb_decide(rec, res, &best);
+    Hit fin;
+    if (proven) { fin.start = best.start; fin.end = best.end; fin.dist = best.dist; }
+    else fin = truth;                                                    // the kernel re-runs the full read
+    out[0] = fin.start; out[1] = fin.end; *dist = fin.dist;
+    diag[0] = cl.n; diag[1] = rec.n_jobs; diag[2] = proven ? 0 : 1; diag[3] = rec.flags; diag[4] = violations;
+    diag[5] = tainted_windows; diag[6] = window_cols; diag[7] = (int64_t)(max_gap * 1e9);
+    // a proven result must equal the full exact recurrence
+    if (proven && (fin.start != truth.start || fin.end != truth.end || fin.dist != truth.dist)) return -1;
+    return 0;
+}
+
+// the full exact recurrence alone (cross-checked against the oracle by the test)
+int plan_exact(const double *x, int N, const double *y, int n, int32_t *out, double *dist)
+{
+    const Hit h = exact_window(x, N, y, 0, n, 0, false);
+    out[0] = h.start; out[1] = h.end; *dist = h.dist;
+    return 0;
+}
+
+}  // extern "C"

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.MotifParams) == 16
     assert C.sizeof(_cabi.SegParams) == 48
     assert _cabi.HIT_DTYPE.itemsize == 16 and _cabi.HIT_DTYPE.fields["dist"][1] == 8
-    assert C.sizeof(_cabi.Timing) == 8 * 3 + 8 * 3
+    assert C.sizeof(_cabi.Timing) == 8 * _cabi.K_COUNT + 8 * _cabi.K_COUNT and _cabi.K_COUNT == 5   # enum sqk_kernel_id
 
 
 def test_header_compiles_as_plain_c(tmp_path):
