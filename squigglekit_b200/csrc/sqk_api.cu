@@ -152,6 +152,7 @@ struct sqk_ctx {
     sqk_timing acc{};
     int force_lanes = 0;
     int dtw_plan = SQK_PLAN_AUTO;
+    int lb_want_k = 20;
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1;
 };
@@ -397,6 +398,37 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
     return SQK_OK;
 }
 
+// Lanes / rows-per-lane of the lower-bound kernel.  Its cells cost 3 instructions, so the per-step overhead
+// (shuffle, ring load, candidate test) weighs more than in the float64 kernel: prefer up to 20 rows per lane.
+static bool pick_lb_shape(const sqk_ctx *c, int N, int *L_out, int *K_out)
+{
+    static const int kmin[4] = {SQK_DTW_L4_KMIN, SQK_DTW_L8_KMIN, SQK_DTW_L16_KMIN, SQK_DTW_L32_KMIN};
+    static const int kmax[4] = {SQK_DTW_L4_KMAX, SQK_DTW_L8_KMAX, SQK_DTW_L16_KMAX, SQK_DTW_L32_KMAX};
+    static const int lanes[4] = {4, 8, 16, 32};
+    static int env_lanes = -1;
+    if (env_lanes < 0) { const char *e = getenv("SQK_LB_LANES"); env_lanes = e ? atoi(e) : 0; }   // experiments
+    const int force = env_lanes ? env_lanes : c->force_lanes;
+    auto fits = [&](int li) {
+        const int L = lanes[li], K = (N + L - 1) / L;
+        return K >= kmin[li] && K <= kmax[li] && K >= 2;
+    };
+    int pick = -1;
+    if (force) {
+        for (int li = 0; li < 4; li++) if (lanes[li] == force && fits(li)) pick = li;
+    }
+    if (pick < 0) {
+        const int want_k = c->lb_want_k;
+        for (int li = 0; li < 4 && pick < 0; li++)
+            if (fits(li) && (N + lanes[li] - 1) / lanes[li] <= want_k) pick = li;
+        for (int li = 0; li < 4 && pick < 0; li++)
+            if (fits(li)) pick = li;
+    }
+    if (pick < 0) return false;
+    *L_out = lanes[pick];
+    *K_out = (N + lanes[pick] - 1) / lanes[pick];
+    return true;
+}
+
 static sqk_lb_launcher pick_lb(int L)
 {
     switch (L) {
@@ -453,7 +485,8 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.hits = d_hits + m; a.hit_stride = n_models;
         a.counter = ctr;
         cudaEvent_t eb;
-        if (L < 4 || !want_two_pass(c, p, N, v.max_len)) {   // motifs of <= 4 points run one thread per read: single pass
+        int LL = 0, LK = 0;   // shape of the lower-bound kernel
+        if (L < 4 || !want_two_pass(c, p, N, v.max_len) || !pick_lb_shape(c, N, &LL, &LK)) {   // motifs of <= 4 points run one thread per read: single pass
             TRY(tick(c, SQK_K_DTW, st, &eb));
             cudaError_t e = fn(K, a, c->n_sms, st);
             if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
@@ -482,8 +515,8 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the fallback
         b.short_len = 2 * (b.W + N);
         TRY(tick(c, SQK_K_DTW_LB, st, &eb));
-        cudaError_t e = pick_lb(L)(K, b, c->n_sms, st);
-        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW lower-bound launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        cudaError_t e = pick_lb(LL)(LK, b, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW lower-bound launch (N=%d, K=%d, L=%d): %s", N, LK, LL, cudaGetErrorString(e));
         TRY(tock(eb, st));
 
         TRY(tick(c, SQK_K_DTW_WIN, st, &eb));

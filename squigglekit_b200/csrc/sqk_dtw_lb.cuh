@@ -15,7 +15,11 @@
 
 #define SQK_LB_WARPS 4
 #define SQK_LB_THREADS (SQK_LB_WARPS * 32)
+#ifdef SQK_LB_MINB_OVERRIDE     // experiments (sqk_ubench variants)
+#define SQK_LB_MINB(K) SQK_LB_MINB_OVERRIDE
+#else
 #define SQK_LB_MINB(K) ((K) <= 10 ? 6 : ((K) <= 16 ? 5 : ((K) <= 20 ? 4 : 2)))
+#endif
 
 struct LbArgs {
     const int16_t *base;      // base[i] = absolute sample i
@@ -38,16 +42,43 @@ struct LbArgs {
     int short_len;            // reads with n_kept <= short_len skip pass 1 (one full-length job)
 };
 
-template <int K, int L, bool RAGGED>
-__device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], const float (&x)[K], const float *ring, int l,
-                                        bool pass0, int t, int n_last, float w, float &bot, float &prev_up,
-                                        float &runmin, float &thr, float aeps, float bslack, LbClusters *cl,
-                                        const int32_t *ck, int n_ref, int64_t cursor0, int W)
+// Shared-memory ring access by 32-bit shared address.  Every group's ring is aligned to its size (RC*4 bytes), so
+// advancing by one entry with wrap-around is one add and one bit-select.
+__device__ __forceinline__ float lb_lds(unsigned addr)
 {
-    constexpr int RC = 16 * L;
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <int RING_BYTES>
+__device__ __forceinline__ unsigned lb_ring_next(unsigned addr)
+{
+    return (addr & ~(unsigned)(RING_BYTES - 1)) | ((addr + 4u) & (unsigned)(RING_BYTES - 1));
+}
+
+// State of the candidate watch of one read (meaningful in the lane that owns the last motif row).
+struct LbWatch {
+    float runmin, thr;     // running minimum of L and its candidate threshold
+    float thr_u;           // thr + an upper bound of (j + N) * w over the current block of steps: the cheap test on U
+                           // (-inf in every other lane)
+    float aeps, bslack, w;
+    int n;                 // columns of the read
+    int N;
+};
+
+// One wavefront step of one lane: column (t - l) of the U recurrence for this lane's K rows (sqk_dtw_plan.cuh).
+// tf == (float)t.  raddr: shared address of this lane's ring entry for this step.
+template <int K, int L, bool RAGGED>
+__device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], const float (&x)[K], unsigned &raddr, int l,
+                                        bool pass0, int t, float &tf, float &bot, float &prev_up, LbWatch &wt,
+                                        LbClusters *cl, const int32_t *ck, int n_ref, int64_t cursor0, int W)
+{
     float up = __shfl_up_sync(SQK_FULL_MASK, bot, 1, L);
-    if (l == 0) up = 0.0f;                             // virtual row above row 0: free start
-    const float y = ring[(t - l) & (RC - 1)];
+    const float virt = sqk_lb_virtual(tf, wt.w);       // free-start row: j*w in column j (lane 0 is at column t)
+    tf = __fadd_rn(tf, 1.0f);
+    if (l == 0) up = virt;
+    const float y = lb_lds(raddr);
+    raddr = lb_ring_next<16 * L * 4>(raddr);
     float dg = prev_up;
     prev_up = up;
     float u = up;
@@ -55,19 +86,23 @@ __device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], co
     for (int k = 0; k < K; k++) {
         const float lf = ci[k];
         const float m = fminf(fminf(u, dg), lf);
-        float nc = sqk_add_rd(sqk_lb_local(x[k], y, w), m);
+        float nc = sqk_lb_cell(x[k], y, m);
         if (RAGGED && k == 0 && pass0) nc = up;        // pass-through slot (only when L*K != N)
         dg = lf;
         u = nc;
         co[k] = nc;
     }
     bot = u;
-    const int j = t - (L - 1);
-    const bool ev = (unsigned)j < (unsigned)n_last && bot <= thr;
-    if (__any_sync(SQK_FULL_MASK, ev)) {
-        if (ev) {
-            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = 8 * L; sc.W = W;
-            lbc_event(*cl, j, bot, runmin, thr, aeps, bslack, sc);
+    if (bot <= wt.thr_u) {                             // rare: a column of the last row that may be a candidate
+        const int j = t - (L - 1);
+        if ((unsigned)j < (unsigned)wt.n) {            // (stale ring entries past the end of the read never count)
+            const float lj = sqk_lb_adjust(bot, j, wt.N, wt.w);
+            if (lj <= wt.thr) {
+                LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = 8 * L; sc.W = W;
+                lbc_event(*cl, j, lj, wt.runmin, wt.thr, wt.aeps, wt.bslack, sc);
+                // the threshold may have moved: keep the cheap test valid for the rest of this block and the next
+                wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(j + wt.N + 16 * L), wt.w));
+            }
         }
     }
 }
@@ -80,7 +115,14 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
     constexpr int S = (L == 1) ? 8 : 7 * L;   // steps between ring refills
     constexpr int CH = 8 * L;          // raw samples fetched per refill
 
-    __shared__ float ring_all[SQK_LB_WARPS * G * RC];
+    // Each group's ring must be aligned to its size (RC*4 bytes) in the shared address space for lb_ring_next; static
+    // shared memory starts behind a reserved kilobyte, so the alignment is established here, not by __align__.
+    __shared__ float ring_raw[SQK_LB_WARPS * G * RC + RC];
+    float *ring_all;
+    {
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(ring_raw);
+        ring_all = ring_raw + (((s0 + RC * 4u - 1u) & ~(RC * 4u - 1u)) - s0) / 4u;
+    }
     __shared__ int32_t ck_all[SQK_LB_WARPS * G * SQK_LB_CKPT];
     __shared__ LbClusters cl_all[SQK_LB_WARPS * G];
 
@@ -109,8 +151,14 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 
     const float inf = __int_as_float(0x7f800000);
     float c[K], c2[K];
-    float bot = inf, prev_up = inf, runmin = inf, thr = inf, w = 0.0f, aeps = 0.0f, bslack = 0.0f;
-    int n = 0, n_last = 0, t = 0, wcount = 0, my_read = -1, n_ref = 0;
+    float bot = inf, prev_up = inf, tf = 0.0f;
+    LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.aeps = 0.0f; wt.bslack = 0.0f; wt.w = 0.0f; wt.n = 0; wt.N = a.N;
+    // groups of one warp start in phase and, with equal-length reads, stay in phase: rotate each group's ring by
+    // 8 banks per lane-group so that their simultaneous reads never share a bank
+    const int rot = (g * L) & (RC - 1);
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    unsigned raddr = ring_s;
+    int n = 0, t = 0, wcount = 0, my_read = -1, n_ref = 0;
     int64_t begin = 0, end = 0, cursor = 0, cursor0 = 0;
     double center = 0.0, scale = 1.0;
     bool done = true, exhausted = false;
@@ -160,16 +208,16 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         }
                     } else {
                         done = false;
-                        n_last = (l == L - 1) ? n : 0;
-                        t = 0; wcount = 0; n_ref = 0;
+                        t = 0; tf = 0.0f; wcount = 0; n_ref = 0;
                         cursor = cursor0;
+                        raddr = ring_s + 4u * (unsigned)((rot - l) & (RC - 1));   // entry of column t - l = -l
 #pragma unroll
                         for (int k = 0; k < K; k++) c[k] = inf;
                         bot = inf;
                         prev_up = (l == 0) ? 0.0f : inf;
-                        runmin = inf; thr = inf;
-                        w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
-                        sqk_lb_slack(a.N, w, &aeps, &bslack);
+                        wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = n;
+                        wt.w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
+                        sqk_lb_slack(a.N, wt.w, &wt.aeps, &wt.bslack);
                         if (l == L - 1) lbc_reset(*cl);
                     }
                 }
@@ -207,7 +255,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                 for (int e = 0; e < 8; e++) {
                     if (keep & (1u << e)) {
                         const double y = __ddiv_rn(__dsub_rn((double)smp.get(e), center), scale);
-                        ring[pos & (RC - 1)] = (float)y;      // round to nearest: |y - y32| <= 2^-24 |y|
+                        ring[(pos + rot) & (RC - 1)] = (float)y;   // round to nearest: |y - y32| <= 2^-24 |y|
                         pos++;
                     }
                 }
@@ -220,19 +268,21 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
         }
         __syncwarp();
 
+        // the cheap candidate test of this block of steps: U <= thr + (largest (j + N) * w of the block)
+        if (l == L - 1 && !done) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + S + a.N), wt.w));
 #pragma unroll 1
         for (int it = 0; it < S; it += 2) {
-            lb_step<K, L, RAGGED>(c, c2, x, ring, l, pass0, t, n_last, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, n_ref, cursor0, a.W);
+            lb_step<K, L, RAGGED>(c, c2, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
             t++;
-            lb_step<K, L, RAGGED>(c2, c, x, ring, l, pass0, t, n_last, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, n_ref, cursor0, a.W);
+            lb_step<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
             t++;
         }
         __syncwarp();
 
         if (!done && t >= n + L - 1) {
             if (l == L - 1) {
-                lbc_finish(*cl, thr);
-                LbRead rec; rec.min_l = runmin; rec.thr = thr; rec.n_jobs = 0; rec.flags = cl->overflow;
+                lbc_finish(*cl, wt.thr);
+                LbRead rec; rec.min_l = wt.runmin; rec.thr = wt.thr; rec.n_jobs = 0; rec.flags = cl->overflow;
                 if (cl->n == 0) rec.flags |= 2;           // cannot happen (the minimum itself is a candidate); be safe
                 for (int q = 0; q < cl->n; q++)
                     if (cl->tainted[q] < 0) rec.flags |= 4;   // its boundary column had already left the checkpoint ring
@@ -250,6 +300,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                 a.reads[my_read] = rec;
             }
             done = true;
+            wt.thr_u = -inf;
         }
     }
 }

@@ -7,10 +7,15 @@
 // result bit for bit, so float32 is only ever used as a *proof*:
 //
 //   pass 1 (sqk_dtw_lb_kernel)  computes for every column j a LOWER BOUND  L[j] <= C[N-1][j]  of the last
-//       row of mlpy's cost matrix: float32, every addition rounded towards -inf, every local cost
-//       |x_i - y_j| replaced by  rz(|x32_i - y32_j|) - w  with  w >= |x_i - x32_i| + |y_j - y32_j|.  By
-//       induction over the recurrence (min and rounding are monotone) L <= C holds cell by cell.  Columns
-//       with  L[j] <= thr = minL + slack  are candidates; neighbouring candidates form clusters.
+//       row of mlpy's cost matrix in float32.  Every local cost satisfies  |x_i - y_j| >= |x32_i - y32_j| - w
+//       with  w >= |x_i - x32_i| + |y_j - y32_j|, and a path that starts in column s and ends in (N-1, j) has at
+//       most  N + (j - s)  cells (N-1 down moves at most, one cell per column move).  So
+//           C[N-1][j]  >=  min over paths ( sum |x32 - y32| + s*w )  -  (j + N) * w .
+//       The kernel runs the recurrence for  U = sum |x32 - y32| + s*w : the free-start row feeds  j*w  instead
+//       of 0, every addition is rounded towards -inf and |x32 - y32| towards zero, so by induction (min and
+//       rounding are monotone) U never exceeds its exact value; then  L[j] = rd(U[N-1][j] - ru((j + N) * w)).
+//       That is 3 instructions per cell (FADD.RZ, FMNMX3, FADD.RM).  Columns with  L[j] <= thr = minL + slack
+//       are candidates; neighbouring candidates form clusters.
 //   pass 2 (sqk_dtw_kernel<JOBS>)  runs the exact float64 recurrence with start pointers on a window
 //       [lo - W - 1, hi] around each cluster.  The window's first column is a boundary: rows >= 1 are set to
 //       cost -1 with the pointer SQK_TAINT.  -1 is strictly below every true cost (costs are >= 0), so every
@@ -76,6 +81,7 @@ SQK_HD float sqk_add_rd(float a, float b) { return __fadd_rd(a, b); }
 SQK_HD float sqk_add_ru(float a, float b) { return __fadd_ru(a, b); }
 SQK_HD float sqk_add_rz(float a, float b) { return __fadd_rz(a, b); }
 SQK_HD float sqk_mul_ru(float a, float b) { return __fmul_ru(a, b); }
+SQK_HD float sqk_mul_rd(float a, float b) { return __fmul_rd(a, b); }
 SQK_HD float sqk_d2f_ru(double a) { return __double2float_ru(a); }
 #else
 static inline float sqk_round_dir(double v, int dir)   // dir: -1 down, +1 up, 0 towards zero; v is exact
@@ -98,6 +104,7 @@ SQK_HD float sqk_add_rd(float a, float b) { return sqk_round_dir((double)a + (do
 SQK_HD float sqk_add_ru(float a, float b) { return sqk_round_dir((double)a + (double)b, 1); }
 SQK_HD float sqk_add_rz(float a, float b) { return sqk_round_dir((double)a + (double)b, 0); }
 SQK_HD float sqk_mul_ru(float a, float b) { return sqk_round_dir((double)a * (double)b, 1); }
+SQK_HD float sqk_mul_rd(float a, float b) { return sqk_round_dir((double)a * (double)b, -1); }
 SQK_HD float sqk_d2f_ru(double a) { return sqk_round_dir(a, 1); }
 #endif
 
@@ -118,11 +125,21 @@ SQK_HD double sqk_lb_ymax(int lo, int hi, double center, double scale)
     return (a > b ? a : b) / s * (1.0 + 1.0 / 1048576.0);
 }
 
-// Lower bound of one local cost: x32, y32 are the round-to-nearest float32 images of x_i, y_j.
-SQK_HD float sqk_lb_local(float x32, float y32, float w)
+// One cell of the U recurrence: x32, y32 are the round-to-nearest float32 images of x_i, y_j; m = min3 of the
+// three predecessors.
+SQK_HD float sqk_lb_cell(float x32, float y32, float m)
 {
     const float t = sqk_add_rz(x32, -y32);        // |t| <= |x32 - y32|
-    return sqk_add_rd(fabsf(t), -w);              // <= |x - y| (may be slightly negative: still a lower bound)
+    return sqk_add_rd(fabsf(t), m);
+}
+
+// What the free-start row feeds into row 0 at column j (a lower bound of j*w), tj = (float)j exactly.
+SQK_HD float sqk_lb_virtual(float tj, float w) { return sqk_mul_rd(tj, w); }
+
+// L[j] from U[N-1][j]: subtract an upper bound of (j + N) * w.
+SQK_HD float sqk_lb_adjust(float u, int j, int N, float w)
+{
+    return sqk_add_rd(u, -sqk_mul_ru((float)(j + N), w));
 }
 
 // Candidate threshold for a running minimum v:  v + (|v| * aeps + b), every step rounded up.
@@ -131,14 +148,24 @@ SQK_HD float sqk_lb_thr(float v, float aeps, float b)
     return sqk_add_ru(v, sqk_add_ru(sqk_mul_ru(fabsf(v), aeps), b));
 }
 
-// slack constants: float32 round-down loses at most one ulp (2^-23 relative) per addition and w per local cost
-// along a path; an alignment of an N-point motif has about N..2N cells.
+// slack constants: float32 round-down loses at most one ulp (2^-23 relative) per addition; the bound charges w
+// for each of up to N + (j - s) cells where the true deficit is usually far smaller; an alignment of an N-point
+// motif has about N..2N cells.
 SQK_HD void sqk_lb_slack(int N, float w, float *aeps, float *b)
 {
     const float cells = (float)(N + 64);
     *aeps = sqk_mul_ru(cells, 1.1920929e-07f);    // 2^-23
-    *b = sqk_mul_ru(sqk_mul_ru(cells, 2.0f), w);
+    *b = sqk_mul_ru(sqk_mul_ru(cells, 3.0f), w);
 }
+
+// The cheap per-step test runs on U:  L[j] = rd(U - off_j) <= thr  implies  U < thr + ulp(thr) + off_j, so with
+// offmax >= off_j for every column of the block,  U <= thr_u  catches every candidate (and a few non-candidates).
+SQK_HD float sqk_lb_thr_u(float thr, float offmax)
+{
+    return sqk_add_ru(sqk_add_ru(thr, sqk_mul_ru(fabsf(thr), 2.4e-7f)), sqk_add_ru(offmax, 1e-30f));
+}
+
+#define SQK_LB_THR_INIT 1e30f                     // threshold before the first column (finite: inf <= thr must be false)
 
 SQK_HD int sqk_lb_window(int N) { return 2 * N + 32; }   // columns in front of a cluster's first candidate
 

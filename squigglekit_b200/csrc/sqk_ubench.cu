@@ -96,9 +96,11 @@ template <int K, int L>
 __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb(int steps, const double *model, float *sink)
 {
     constexpr int G = 32 / L, RC = 16 * L;
-    __shared__ float ring_all[SQK_LB_WARPS * G * RC];
+    __shared__ float ring_raw[SQK_LB_WARPS * G * RC + RC];
     __shared__ LbClusters cl_all[SQK_LB_WARPS * G];
     __shared__ int32_t ck_all[SQK_LB_WARPS * G * SQK_LB_CKPT];
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(ring_raw);
+    float *ring_all = ring_raw + (((s0 + RC * 4u - 1u) & ~(RC * 4u - 1u)) - s0) / 4u;
     const int lane = threadIdx.x & 31, l = lane % L, g = lane / L;
     const int gid = (threadIdx.x >> 5) * G + g;
     float *ring = ring_all + gid * RC;
@@ -112,15 +114,17 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb(int step
     const float inf = __int_as_float(0x7f800000);
 #pragma unroll
     for (int k = 0; k < K; k++) { x[k] = (float)model[(l * K + k) % 80]; c[k] = inf; }
-    float bot = inf, prev_up = (l == 0) ? 0.0f : inf, runmin = inf, thr = inf, aeps = 0.0f, bslack = 0.0f;
-    const float w = sqk_lb_width(2.0, 8.0);
-    sqk_lb_slack(80, w, &aeps, &bslack);
-    const int n = (l == L - 1) ? steps : 0;
+    float bot = inf, prev_up = (l == 0) ? 0.0f : inf, tf = 0.0f;
+    LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = steps; wt.N = 80;
+    wt.w = sqk_lb_width(2.0, 8.0);
+    sqk_lb_slack(80, wt.w, &wt.aeps, &wt.bslack);
+    unsigned raddr = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)((g * L - l) & (RC - 1));
     for (int t = 0; t < steps; t += 2) {
-        lb_step<K, L, false>(c, c2, x, ring, l, false, t, n, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, t / 64, 0, 192);
-        lb_step<K, L, false>(c2, c, x, ring, l, false, t + 1, n, w, bot, prev_up, runmin, thr, aeps, bslack, cl, ck, t / 64, 0, 192);
+        if ((t % (7 * L)) == 0 && l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 7 * L + 80), wt.w));
+        lb_step<K, L, false>(c, c2, x, raddr, l, false, t, tf, bot, prev_up, wt, cl, ck, t / 64, 0, 192);
+        lb_step<K, L, false>(c2, c, x, raddr, l, false, t + 1, tf, bot, prev_up, wt, cl, ck, t / 64, 0, 192);
     }
-    float acc = runmin + thr + (float)cl->n;
+    float acc = wt.runmin + wt.thr + (float)cl->n;
 #pragma unroll
     for (int k = 0; k < K; k++) acc += c[k];
     if (acc == 123456.789f) sink[0] = acc;
@@ -227,7 +231,7 @@ static void run_dtw(const char *prec, int sms, const double *d_model, void *d_si
 }
 
 // ---- individual pipes: ILP independent chains per thread, enough warps to saturate ----------------
-enum { OP_DADD, OP_DSETP_FSEL, OP_FSEL, OP_SEL, OP_SHFL, OP_FADD, OP_IMAD, OP_FMNMX };
+enum { OP_DADD, OP_DSETP_FSEL, OP_FSEL, OP_SEL, OP_SHFL, OP_FADD, OP_IMAD, OP_FMNMX, OP_FADD_RM, OP_FADD_RZ_ABS, OP_FMNMX3, OP_LBCELL };
 
 template <int OP>
 __global__ void __launch_bounds__(256) ub_pipe(int iters, double *sink, int seed)
@@ -248,6 +252,10 @@ __global__ void __launch_bounds__(256) ub_pipe(int iters, double *sink, int seed
             if (OP == OP_FADD) f[i] = __fadd_rn(f[i], (float)inc);
             if (OP == OP_IMAD) v[i] = v[i] * seed + it;
             if (OP == OP_FMNMX) f[i] = fminf(f[i], f[(i + 3) % C] + 0.0f);
+            if (OP == OP_FADD_RM) f[i] = __fadd_rd(f[i], (float)inc);
+            if (OP == OP_FADD_RZ_ABS) f[i] = __fadd_rz(fabsf(f[i]), -(float)inc);
+            if (OP == OP_FMNMX3) f[i] = fminf(fminf(f[i], f[(i + 3) % C]), f[(i + 5) % C]);
+            if (OP == OP_LBCELL) f[i] = __fadd_rd(__fadd_rd(fabsf(__fadd_rz(f[(i + 1) % C], -(float)inc)), -1e-7f), fminf(fminf(f[i], f[(i + 3) % C]), f[(i + 5) % C]));
         }
     }
     double acc = 0;
@@ -322,6 +330,10 @@ int main(int argc, char **argv)
         run_pipe<OP_FADD>("FADD", sms, clk, d_sink);
         run_pipe<OP_IMAD>("IMAD", sms, clk, d_sink);
         run_pipe<OP_FMNMX>("FADD+FMNMX", sms, clk, d_sink);
+        run_pipe<OP_FADD_RM>("FADD.RM", sms, clk, d_sink);
+        run_pipe<OP_FADD_RZ_ABS>("FADD.RZ|abs|", sms, clk, d_sink);
+        run_pipe<OP_FMNMX3>("FMNMX3", sms, clk, d_sink);
+        run_pipe<OP_LBCELL>("lb cell (FADD.RZ+FADD.RM+FMNMX3+FADD.RM), 8 independent chains", sms, clk, d_sink);
     }
     return 0;
 }

@@ -77,37 +77,48 @@ int plan_two_pass(const double *x, int N, const double *y, int n, const uint8_t 
     std::vector<float> x32(N), c(N, inf), nc(N);
     for (int i = 0; i < N; i++) x32[i] = (float)x[i];
     LbClusters cl; lbc_reset(cl);
-    float runmin = inf, thr = inf;
+    float runmin = inf, thr = SQK_LB_THR_INIT;
     int32_t ck[SQK_LB_CKPT];
     int n_ref = 0, wcount = 0, raw = -align_off;       // raw: position of the next refill relative to the read's first sample
     int64_t violations = 0; double max_gap = 0.0;
+    const int lanes = ch / 8, S = lanes == 1 ? 8 : 7 * lanes;
+    float thr_u = -inf, prev_virt = 0.0f;
+    int64_t missed = 0;
     for (int j = 0; j < n; j++) {
         // the kernel refills ahead of use (whenever fewer than S columns are buffered beyond the wavefront)
-        const int lanes = ch / 8, S = lanes == 1 ? 8 : 7 * lanes;
         while (wcount < j + lanes + S && raw < raw_len) {
             ck[n_ref % SQK_LB_CKPT] = wcount; n_ref++;
             for (int e = 0; e < ch; e++) { const int r = raw + e; if (r >= 0 && r < raw_len && keep[r]) wcount++; }
             raw += ch;
         }
+        // the lane that owns the last row sees column j at step t = j + lanes - 1; blocks of S steps share one thr_u
+        const int t = j + lanes - 1;
+        if (j == 0 || t % S == 0) thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(t - t % S + S + N), w));
         const float y32 = (float)y[j];
+        const float virt = sqk_lb_virtual((float)j, w);
         for (int i = 0; i < N; i++) {
             float m;
-            if (i == 0) m = 0.0f;
+            if (i == 0) m = std::fmin(std::fmin(virt, prev_virt), j == 0 ? inf : c[0]);   // free-start row: j*w, (j-1)*w, left
             else {
                 const float dg = j == 0 ? inf : c[i - 1], lf = j == 0 ? inf : c[i], up = nc[i - 1];
                 m = std::fmin(std::fmin(up, dg), lf);
             }
-            nc[i] = sqk_add_rd(sqk_lb_local(x32[i], y32, w), m);
+            nc[i] = sqk_lb_cell(x32[i], y32, m);
         }
+        prev_virt = virt;
         c.swap(nc);
-        const float v = c[N - 1];
+        const float u = c[N - 1];
+        const float v = sqk_lb_adjust(u, j, N, w);
         if (!((double)v <= crow[j])) violations++;
         if (crow[j] - (double)v > max_gap && crow[j] <= truth.dist + 1.0) max_gap = crow[j] - (double)v;
-        if (v <= thr) {
+        if (v <= thr && !(u <= thr_u)) missed++;      // the cheap test must never miss a candidate
+        if (u <= thr_u && v <= thr) {
             LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = -(int64_t)align_off; sc.ch = ch; sc.W = W;
             lbc_event(cl, j, v, runmin, thr, aeps, bslack, sc);
+            thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(j + N + 2 * ch), w));
         }
     }
+    violations += missed;
     lbc_finish(cl, thr);
     LbRead rec; rec.min_l = runmin; rec.thr = thr; rec.n_jobs = 0; rec.flags = cl.overflow;
     if (cl.n == 0) rec.flags |= 2;
