@@ -195,7 +195,7 @@ def alu_peak_cells_per_s(which="dtw_step", prec="fp64"):
             d = json.loads(ln)
         except Exception:
             continue
-        if d.get("bench") == which and d.get("precision") == prec:
+        if d.get("bench") in which.split("|") and d.get("precision") == prec:
             best = max(best or 0.0, float(d["cells_per_s"]))
     return best, src
 
@@ -330,7 +330,7 @@ def main():
         two_pass = kt["dtw_lb"]["launches"] > 0
         if two_pass:
             # dominant kernel: the float32 lower-bound scan (every sample of every read goes through it once)
-            kname, kkey, ub, ubp = "sqk_dtw_lb_kernel", "dtw_lb", "lb_step", "fp32_rd"
+            kname, kkey, ub, ubp = "sqk_dtw_lb_kernel", "dtw_lb", "lb_step|lb_step2", "fp32_rd"
         else:
             kname, kkey, ub, ubp = "sqk_dtw_kernel", "dtw", "dtw_step", "fp64" if args.precision == "fp64" else "fp32"
         dtw_launches = max(1, kt[kkey]["launches"])

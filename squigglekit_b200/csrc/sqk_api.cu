@@ -152,7 +152,7 @@ struct sqk_ctx {
     sqk_timing acc{};
     int force_lanes = 0;
     int dtw_plan = SQK_PLAN_AUTO;
-    int lb_want_k = 20;
+    int lb_want_k = 12;   // measured on B200: K=10/L=8 5.85 ms vs K=20/L=4 6.11 ms per 100k x 4096 x 80
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1;
 };
@@ -398,8 +398,8 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
     return SQK_OK;
 }
 
-// Lanes / rows-per-lane of the lower-bound kernel.  Its cells cost 3 instructions, so the per-step overhead
-// (shuffle, ring load, candidate test) weighs more than in the float64 kernel: prefer up to 20 rows per lane.
+// Lanes / rows-per-lane of the lower-bound kernel: same policy as the float64 kernel (fewest lanes with <= 12 rows per
+// lane); SQK_LB_LANES overrides it for experiments.
 static bool pick_lb_shape(const sqk_ctx *c, int N, int *L_out, int *K_out)
 {
     static const int kmin[4] = {SQK_DTW_L4_KMIN, SQK_DTW_L8_KMIN, SQK_DTW_L16_KMIN, SQK_DTW_L32_KMIN};

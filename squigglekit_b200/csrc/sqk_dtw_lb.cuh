@@ -66,6 +66,20 @@ struct LbWatch {
     int N;
 };
 
+__device__ __forceinline__ void lb_candidate(float u, int j, LbWatch &wt, LbClusters *cl, const int32_t *ck, int n_ref,
+                                             int64_t cursor0, int ch, int W)
+{
+    if (u <= wt.thr_u && (unsigned)j < (unsigned)wt.n) {   // (stale ring entries past the end of the read never count)
+        const float lj = sqk_lb_adjust(u, j, wt.N, wt.w);
+        if (lj <= wt.thr) {
+            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = ch; sc.W = W;
+            lbc_event(*cl, j, lj, wt.runmin, wt.thr, wt.aeps, wt.bslack, sc);
+            // the threshold may have moved: keep the cheap test valid for the rest of this block and the next
+            wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(j + wt.N + 2 * ch), wt.w));
+        }
+    }
+}
+
 // One wavefront step of one lane: column (t - l) of the U recurrence for this lane's K rows (sqk_dtw_plan.cuh).
 // tf == (float)t.  raddr: shared address of this lane's ring entry for this step.
 template <int K, int L, bool RAGGED>
@@ -93,17 +107,57 @@ __device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], co
         co[k] = nc;
     }
     bot = u;
-    if (bot <= wt.thr_u) {                             // rare: a column of the last row that may be a candidate
-        const int j = t - (L - 1);
-        if ((unsigned)j < (unsigned)wt.n) {            // (stale ring entries past the end of the read never count)
-            const float lj = sqk_lb_adjust(bot, j, wt.N, wt.w);
-            if (lj <= wt.thr) {
-                LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = 8 * L; sc.W = W;
-                lbc_event(*cl, j, lj, wt.runmin, wt.thr, wt.aeps, wt.bslack, sc);
-                // the threshold may have moved: keep the cheap test valid for the rest of this block and the next
-                wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(j + wt.N + 16 * L), wt.w));
-            }
-        }
+    if (bot <= wt.thr_u)                               // rare: a column of the last row that may be a candidate
+        lb_candidate(bot, t - (L - 1), wt, cl, ck, n_ref, cursor0, 8 * L, W);
+}
+
+__device__ __forceinline__ float2 lb_lds2(unsigned addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+template <int RING_BYTES>
+__device__ __forceinline__ unsigned lb_ring_next2(unsigned addr)
+{
+    return (addr & ~(unsigned)(RING_BYTES - 1)) | ((addr + 8u) & (unsigned)(RING_BYTES - 1));
+}
+
+// Two columns per step: this lane's K rows of columns j = t - 2l (cells A) and j + 1 (cells B).  B_k needs A_k, A_{k-1}
+// and B_{k-1}; A_k needs A_{k-1}: two dependency chains one cell apart, so the lane always has two independent
+// FMNMX3 -> FADD pairs in flight (the one-column step is latency-bound on a single chain).  tf == (float)t.
+template <int K, int L, bool RAGGED>
+__device__ __forceinline__ void lb_step2(const float (&ci)[K], float (&co)[K], const float (&x)[K], unsigned &raddr, int l,
+                                         bool pass0, int t, float &tf, float &bot_a, float &bot_b, float &prev_up_b,
+                                         LbWatch &wt, LbClusters *cl, const int32_t *ck, int n_ref, int64_t cursor0, int W)
+{
+    float up_a = __shfl_up_sync(SQK_FULL_MASK, bot_a, 1, L);
+    float up_b = __shfl_up_sync(SQK_FULL_MASK, bot_b, 1, L);
+    const float virt_a = sqk_lb_virtual(tf, wt.w);      // free-start row: j*w in column j (lane 0 is at columns t, t+1)
+    const float virt_b = sqk_lb_virtual(__fadd_rn(tf, 1.0f), wt.w);
+    tf = __fadd_rn(tf, 2.0f);
+    if (l == 0) { up_a = virt_a; up_b = virt_b; }
+    const float2 y = lb_lds2(raddr);
+    raddr = lb_ring_next2<16 * L * 4>(raddr);
+    float dg_a = prev_up_b;                              // row above, column j-1
+    prev_up_b = up_b;
+    float ua = up_a, ub = up_b;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float lf = ci[k];                          // column j-1
+        float a = sqk_lb_cell(x[k], y.x, fminf(fminf(ua, dg_a), lf));
+        if (RAGGED && k == 0 && pass0) a = up_a;         // pass-through slot (only when L*K != N)
+        float b = sqk_lb_cell(x[k], y.y, fminf(fminf(ub, ua), a));
+        if (RAGGED && k == 0 && pass0) b = up_b;
+        dg_a = lf;
+        ua = a; ub = b;
+        co[k] = b;
+    }
+    bot_a = ua; bot_b = ub;
+    if (fminf(ua, ub) <= wt.thr_u) {                     // rare: a column of the last row that may be a candidate
+        const int j = t - 2 * (L - 1);
+        lb_candidate(ua, j, wt, cl, ck, n_ref, cursor0, 8 * L, W);
+        lb_candidate(ub, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, W);
     }
 }
 
@@ -112,8 +166,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 {
     constexpr int G = 32 / L;          // reads per warp
     constexpr int RC = 16 * L;         // ring capacity (entries), power of two
-    constexpr int S = (L == 1) ? 8 : 7 * L;   // steps between ring refills
+    constexpr int COLS = SQK_LB_COLS;
+    constexpr int LAG = COLS * (L - 1);      // columns the last lane runs behind lane 0
+    // columns between ring refills: S + CH + LAG <= RC so that no entry is overwritten before its last reader
+    constexpr int S = (L == 1) ? 8 : (COLS == 2 ? 6 * L : 7 * L);
     constexpr int CH = 8 * L;          // raw samples fetched per refill
+    static_assert(S % (2 * COLS) == 0 && S + CH + LAG <= RC, "ring schedule");
 
     // Each group's ring must be aligned to its size (RC*4 bytes) in the shared address space for lb_ring_next; static
     // shared memory starts behind a reserved kilobyte, so the alignment is established here, not by __align__.
@@ -151,7 +209,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 
     const float inf = __int_as_float(0x7f800000);
     float c[K], c2[K];
-    float bot = inf, prev_up = inf, tf = 0.0f;
+    float bot = inf, bot_b = inf, prev_up = inf, tf = 0.0f;   // COLS == 2: bot is column A's bottom, prev_up is column B's
     LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.aeps = 0.0f; wt.bslack = 0.0f; wt.w = 0.0f; wt.n = 0; wt.N = a.N;
     // groups of one warp start in phase and, with equal-length reads, stay in phase: rotate each group's ring by
     // 8 banks per lane-group so that their simultaneous reads never share a bank
@@ -210,10 +268,10 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         done = false;
                         t = 0; tf = 0.0f; wcount = 0; n_ref = 0;
                         cursor = cursor0;
-                        raddr = ring_s + 4u * (unsigned)((rot - l) & (RC - 1));   // entry of column t - l = -l
+                        raddr = ring_s + 4u * (unsigned)((rot - COLS * l) & (RC - 1));   // entry of column t - COLS*l
 #pragma unroll
                         for (int k = 0; k < K; k++) c[k] = inf;
-                        bot = inf;
+                        bot = inf; bot_b = inf;
                         prev_up = (l == 0) ? 0.0f : inf;
                         wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = n;
                         wt.w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
@@ -270,16 +328,26 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 
         // the cheap candidate test of this block of steps: U <= thr + (largest (j + N) * w of the block)
         if (l == L - 1 && !done) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + S + a.N), wt.w));
+        if constexpr (COLS == 2) {
 #pragma unroll 1
-        for (int it = 0; it < S; it += 2) {
-            lb_step<K, L, RAGGED>(c, c2, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
-            t++;
-            lb_step<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
-            t++;
+            for (int it = 0; it < S; it += 4) {
+                lb_step2<K, L, RAGGED>(c, c2, x, raddr, l, pass0, t, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
+                t += 2;
+                lb_step2<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
+                t += 2;
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < S; it += 2) {
+                lb_step<K, L, RAGGED>(c, c2, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
+                t++;
+                lb_step<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t, tf, bot, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
+                t++;
+            }
         }
         __syncwarp();
 
-        if (!done && t >= n + L - 1) {
+        if (!done && t >= n + LAG) {
             if (l == L - 1) {
                 lbc_finish(*cl, wt.thr);
                 LbRead rec; rec.min_l = wt.runmin; rec.thr = wt.thr; rec.n_jobs = 0; rec.flags = cl->overflow;

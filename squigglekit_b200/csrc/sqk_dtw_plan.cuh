@@ -38,6 +38,9 @@
 #define SQK_HD inline
 #endif
 
+#ifndef SQK_LB_COLS
+#define SQK_LB_COLS 2             // signal columns per wavefront step of the lower-bound kernel (1: lb_step, 2: lb_step2)
+#endif
 #define SQK_TAINT (-7)            // start pointer of a cell that derives from a window boundary
 #define SQK_LB_MAX_CLUSTERS 4     // candidate clusters kept per read; more -> fallback
 #define SQK_LB_GAP 16             // candidate columns at most this far apart share one window

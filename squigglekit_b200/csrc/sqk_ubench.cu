@@ -130,6 +130,70 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb(int step
     if (acc == 123456.789f) sink[0] = acc;
 }
 
+// two columns per step (lb_step2)
+template <int K, int L>
+__global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb2(int steps, const double *model, float *sink)
+{
+    constexpr int G = 32 / L, RC = 16 * L;
+    __shared__ float ring_raw[SQK_LB_WARPS * G * RC + RC];
+    __shared__ LbClusters cl_all[SQK_LB_WARPS * G];
+    __shared__ int32_t ck_all[SQK_LB_WARPS * G * SQK_LB_CKPT];
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(ring_raw);
+    float *ring_all = ring_raw + (((s0 + RC * 4u - 1u) & ~(RC * 4u - 1u)) - s0) / 4u;
+    const int lane = threadIdx.x & 31, l = lane % L, g = lane / L;
+    const int gid = (threadIdx.x >> 5) * G + g;
+    float *ring = ring_all + gid * RC;
+    LbClusters *cl = cl_all + gid;
+    int32_t *ck = ck_all + gid * SQK_LB_CKPT;
+    for (int q = l; q < SQK_LB_CKPT; q += L) ck[q] = q * 60;
+    for (int q = l; q < RC; q += L) ring[q] = (float)(((q * 2654435761u) >> 20) & 1023) * (1.0f / 256) - 2.0f;
+    if (l == L - 1) lbc_reset(*cl);
+    __syncwarp();
+    float x[K], c[K], c2[K];
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < K; k++) { x[k] = (float)model[(l * K + k) % 80]; c[k] = inf; }
+    float bot_a = inf, bot_b = inf, prev_up_b = (l == 0) ? 0.0f : inf, tf = 0.0f;
+    LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = steps; wt.N = 80;
+    wt.w = sqk_lb_width(2.0, 8.0);
+    sqk_lb_slack(80, wt.w, &wt.aeps, &wt.bslack);
+    unsigned raddr = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)((g * L - 2 * l) & (RC - 1));
+    for (int t = 0; t < steps; t += 4) {
+        if ((t % (6 * L)) == 0 && l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 6 * L + 80), wt.w));
+        lb_step2<K, L, false>(c, c2, x, raddr, l, false, t, tf, bot_a, bot_b, prev_up_b, wt, cl, ck, t / 64, 0, 192);
+        lb_step2<K, L, false>(c2, c, x, raddr, l, false, t + 2, tf, bot_a, bot_b, prev_up_b, wt, cl, ck, t / 64, 0, 192);
+    }
+    float acc = wt.runmin + wt.thr + (float)cl->n;
+#pragma unroll
+    for (int k = 0; k < K; k++) acc += c[k];
+    if (acc == 123456.789f) sink[0] = acc;
+}
+
+template <int K, int L>
+static void run_lb2(int sms, const double *d_model, void *d_sink)
+{
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ub_lb2<K, L>, SQK_LB_THREADS, 0));
+    const int grid = sms * occ, steps = 8192;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    ub_lb2<K, L><<<grid, SQK_LB_THREADS>>>(256, d_model, (float *)d_sink);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(a));
+        ub_lb2<K, L><<<grid, SQK_LB_THREADS>>>(steps, d_model, (float *)d_sink);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double cells = (double)grid * SQK_LB_THREADS * K * steps;
+    printf("{\"bench\": \"lb_step2\", \"precision\": \"fp32_rd\", \"K\": %d, \"L\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, "
+           "\"cells_per_s\": %.4e}\n", K, L, occ, best_ms, cells / (best_ms * 1e-3));
+    fflush(stdout);
+}
+
 template <int K, int L>
 static void run_lb(int sms, const double *d_model, void *d_sink)
 {
@@ -302,6 +366,9 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&d_sink, 64));
     CK(cudaMemcpy(d_model, model.data(), 80 * sizeof(double), cudaMemcpyHostToDevice));
     printf("{\"bench\": \"device\", \"sms\": %d, \"clock_khz\": %d}\n", sms, clk);
+    run_lb2<10, 8>(sms, d_model, d_sink);
+    run_lb2<20, 4>(sms, d_model, d_sink);
+    run_lb2<5, 16>(sms, d_model, d_sink);
     run_lb<10, 8>(sms, d_model, d_sink);
     run_lb<20, 4>(sms, d_model, d_sink);
     run_lb<5, 16>(sms, d_model, d_sink);

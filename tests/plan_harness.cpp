@@ -81,19 +81,21 @@ int plan_two_pass(const double *x, int N, const double *y, int n, const uint8_t 
     int32_t ck[SQK_LB_CKPT];
     int n_ref = 0, wcount = 0, raw = -align_off;       // raw: position of the next refill relative to the read's first sample
     int64_t violations = 0; double max_gap = 0.0;
-    const int lanes = ch / 8, S = lanes == 1 ? 8 : 7 * lanes;
+    // the kernel's schedule: blocks of S columns between refills, the last lane LAG columns behind lane 0
+    const int lanes = ch / 8, cols = SQK_LB_COLS, LAG = cols * (lanes - 1);
+    const int S = lanes == 1 ? 8 : (cols == 2 ? 6 * lanes : 7 * lanes);
     float thr_u = -inf, prev_virt = 0.0f;
     int64_t missed = 0;
     for (int j = 0; j < n; j++) {
         // the kernel refills ahead of use (whenever fewer than S columns are buffered beyond the wavefront)
-        while (wcount < j + lanes + S && raw < raw_len) {
+        while (wcount < j + LAG + 1 + S && raw < raw_len) {
             ck[n_ref % SQK_LB_CKPT] = wcount; n_ref++;
             for (int e = 0; e < ch; e++) { const int r = raw + e; if (r >= 0 && r < raw_len && keep[r]) wcount++; }
             raw += ch;
         }
         // the lane that owns the last row sees column j at step t = j + lanes - 1; blocks of S steps share one thr_u
-        const int t = j + lanes - 1;
-        if (j == 0 || t % S == 0) thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(t - t % S + S + N), w));
+        const int t = j - j % cols + LAG;
+        if (j == 0 || (t % S == 0 && j % cols == 0)) thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(t - t % S + S + N), w));
         const float y32 = (float)y[j];
         const float virt = sqk_lb_virtual((float)j, w);
         for (int i = 0; i < N; i++) {
