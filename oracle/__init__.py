@@ -9,7 +9,10 @@ pinned against sklearn / numpy / the reference's own ``segmenter.py`` run in the
 container; the DTW is a restatement of un-vendored mlpy 3.5.0 -> "parity unpinned" there.
 """
 from .cpu import (  # noqa: F401
+    AdapterCfg,
     SegCfg,
+    adapter_batch,
+    adapter_seg,
     build,
     convert_to_pa,
     dtw_subsequence,

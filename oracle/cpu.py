@@ -54,6 +54,28 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+class _AdapterCfg(C.Structure):
+    _fields_ = [("error", C.c_int32), ("no_err_thresh", C.c_int32), ("corrector", C.c_int32), ("window", C.c_int32),
+                ("seg_dist", C.c_int32), ("t_start", C.c_int32), ("t_end", C.c_int32), ("std_scale", C.c_double)]
+
+
+@dataclass
+class AdapterCfg:
+    """The constants hard-coded in the slow5 branch of dRNA_segmenter.py (:81-106)."""
+    error: int = 5
+    no_err_thresh: int = 2500
+    corrector: int = 1200
+    window: int = 100
+    seg_dist: int = 1200
+    t_start: int = 1000
+    t_end: int = 5000
+    std_scale: float = 0.8
+
+    def c(self) -> _AdapterCfg:
+        return _AdapterCfg(self.error, self.no_err_thresh, self.corrector, self.window, self.seg_dist, self.t_start,
+                           self.t_end, self.std_scale)
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
@@ -81,6 +103,8 @@ def lib() -> C.CDLL:
                                              C.c_void_p, ip]
         L.orc_segmenter_batch_f64.argtypes = [dp, lp, C.c_int64, C.POINTER(_SegCfg), C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, ip, ip]
+        L.orc_adapter_seg.argtypes = [dp, C.c_int64, C.POINTER(_AdapterCfg), ip, dp]
+        L.orc_adapter_batch.argtypes = [C.c_void_p, lp, C.c_int64, C.POINTER(_AdapterCfg), C.c_int, C.c_int, C.c_int, ip, ip]
         _lib = L
     return _lib
 
@@ -259,3 +283,30 @@ def segmenter_batch_f64(signals, offsets, cfg: SegCfg = SegCfg(), lim_lo=0, lim_
     if rc:
         raise RuntimeError("orc_segmenter_batch_f64 failed")
     return segs, nsegs
+
+
+def adapter_seg(sig, cfg: AdapterCfg = AdapterCfg(), want_thresholds: bool = False):
+    """dRNA_segmenter.py slow5 branch on one post-outlier signal -> [start, end] of the first segment or None."""
+    v = np.ascontiguousarray(sig, dtype=np.float64)
+    out = np.zeros(2, dtype=np.int32)
+    thr = np.zeros(3, dtype=np.float64)
+    c = cfg.c()
+    got = lib().orc_adapter_seg(_dp(v), v.size, C.byref(c), _ip(out), _dp(thr))
+    if got < 0:
+        raise RuntimeError("orc_adapter_seg failed")
+    seg = [int(out[0]), int(out[1])] if got else None
+    return (seg, thr) if want_thresholds else seg
+
+
+def adapter_batch(signals, offsets, cfg: AdapterCfg = AdapterCfg(), lim_lo=0, lim_hi=1200, n_threads=0):
+    """Per read: scale_outliers -> adapter_seg.  -> (segs[n,2], found[n])."""
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    segs = np.zeros((n, 2), dtype=np.int32)
+    found = np.zeros(n, dtype=np.int32)
+    c = cfg.c()
+    rc = lib().orc_adapter_batch(signals.ctypes.data, _lp(offsets), n, C.byref(c), lim_lo, lim_hi, n_threads, _ip(segs), _ip(found))
+    if rc:
+        raise RuntimeError("orc_adapter_batch failed")
+    return segs, found

@@ -365,6 +365,107 @@ ORC_API int orc_get_segs(const double *sig, int64_t n, const orc_seg_cfg *cfg,
 }
 
 /* ------------------------------------------------------------------------------------
+ * dRNA_segmenter.py, slow5 branch (dRNA_segmenter.py:86-176): the adapter-stall finder.  sig is the
+ * post-outlier signal (scale_outliers with the fixed window (0, 1200), :331-334) as float64.
+ *   median, stdev over sig[t_start:t_end] (:104-105; an empty slice gives NaN and nothing is ever in range);
+ *   top = median + stdev * std_scale (:106);  in range  <=>  a < top  (one-sided, :110);
+ *   state machine :108-166 -- unlike get_segs: err is reset when a run opens (:115), tolerated
+ *   out-of-range samples only count as errors from position no_err_thresh on (:127-129), w is a constant,
+ *   and the scan stops once a closed segment lies more than seg_dist behind (:154-161).
+ * Only the first segment is printed (:171-174): returns 1 and writes out[0..1] = start, end, else 0.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t error, no_err_thresh, corrector, window, seg_dist, t_start, t_end;
+    double std_scale;
+} orc_adapter_cfg;
+
+ORC_API int orc_adapter_seg(const double *sig, int64_t n, const orc_adapter_cfg *cfg, int32_t *out,
+                            double *thr /* top, median, stdev or NULL */)
+{
+    int64_t s0 = cfg->t_start < n ? cfg->t_start : n, s1 = cfg->t_end < n ? cfg->t_end : n;
+    if (s0 < 0) s0 = 0;
+    if (s1 < s0) s1 = s0;
+    const int64_t ns = s1 - s0;
+    double top = NAN, median = NAN, stdev = NAN;
+    if (ns > 0) {
+        double *t = (double *)malloc((size_t)ns * sizeof(double));
+        if (!t) return -1;
+        median = np_median(sig + s0, ns, t);
+        const double mean = np_pairwise(sig + s0, ns) / (double)ns;
+        for (int64_t i = 0; i < ns; i++) { const double d = sig[s0 + i] - mean; t[i] = d * d; }
+        stdev = sqrt(np_pairwise(t, ns) / (double)ns);
+        free(t);
+        top = median + stdev * cfg->std_scale;
+    }
+    if (thr) { thr[0] = top; thr[1] = median; thr[2] = stdev; }
+
+    int open = 0, have = 0;
+    int64_t err = 0, run_err = 0, c = 0, start = 0;
+    int64_t first_start = 0, first_end = 0, last_end = 0;
+    int nseg = 0;
+    const int64_t w = cfg->corrector;
+    for (int64_t i = 0; i < n; i++) {
+        const double a = sig[i];
+        if (a < top) {
+            if (!open) { start = i; open = 1; err = 0; }
+            c++;
+            run_err = 0;
+            if (c >= cfg->window && c >= w && w != 0 && (c % w) == 0) err--;
+        } else if (open && err < cfg->error) {
+            c++;
+            if (i >= cfg->no_err_thresh) { err++; run_err++; }
+            if (c >= cfg->window && c >= w && w != 0 && (c % w) == 0) err--;
+        } else if (open) {
+            if (c >= cfg->window) {
+                const int64_t end = i - run_err;
+                if (nseg > 0 && start - last_end < cfg->seg_dist) {
+                    last_end = end;
+                    if (nseg == 1) first_end = end;
+                } else {
+                    nseg++;
+                    last_end = end;
+                    if (nseg == 1) { first_start = start; first_end = end; have = 1; }
+                }
+            }
+            open = 0; c = 0; err = 0; run_err = 0;
+        } else if (nseg > 0 && i - last_end > cfg->seg_dist) {
+            break;
+        }
+    }
+    if (have) { out[0] = (int32_t)first_start; out[1] = (int32_t)first_end; }
+    return have;
+}
+
+/* per read: scale_outliers (0, 1200) -> orc_adapter_seg.  found[r] = 1/0, segs[r] = (start, end). */
+ORC_API int orc_adapter_batch(const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                              const orc_adapter_cfg *cfg, int lim_lo, int lim_hi, int n_threads,
+                              int32_t *segs, int32_t *found)
+{
+    int failed = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        int got = 0;
+        segs[2 * r] = 0; segs[2 * r + 1] = 0;
+        if (len > 0) {
+            double *y = (double *)malloc((size_t)len * sizeof(double));
+            if (!y) failed = 1;
+            else {
+                const int64_t kept = orc_scale_outliers_i16(signals + offsets[r], len, lim_lo, lim_hi, y);
+                got = orc_adapter_seg(y, kept, cfg, segs + 2 * r, NULL);
+                if (got < 0) { failed = 1; got = 0; }
+                free(y);
+            }
+        }
+        found[r] = got;
+    }
+    return failed ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Batch drivers (OpenMP over reads) -- the "reference arm" / cpu_baseline of bench.py and
  * the large-set parity checker.  Per read they do exactly what the reference's main loop
  * does: scale_outliers -> normalise -> dtw_subsequence -> (start,end,dist).
