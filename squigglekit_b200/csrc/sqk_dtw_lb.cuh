@@ -81,16 +81,15 @@ __device__ __forceinline__ void lb_candidate(float u, int j, LbWatch &wt, LbClus
 }
 
 // One wavefront step of one lane: column (t - l) of the U recurrence for this lane's K rows (sqk_dtw_plan.cuh).
-// tf == (float)t.  raddr: shared address of this lane's ring entry for this step.
+// tf: what the free-start row holds in column t (sqk_lb_virtual).  raddr: shared address of this lane's ring entry.
 template <int K, int L, bool RAGGED>
 __device__ __forceinline__ void lb_step(const float (&ci)[K], float (&co)[K], const float (&x)[K], unsigned &raddr, int l,
                                         bool pass0, int t, float &tf, float &bot, float &prev_up, LbWatch &wt,
                                         LbClusters *cl, const int32_t *ck, int n_ref, int64_t cursor0, int W)
 {
     float up = __shfl_up_sync(SQK_FULL_MASK, bot, 1, L);
-    const float virt = sqk_lb_virtual(tf, wt.w);       // free-start row: j*w in column j (lane 0 is at column t)
-    tf = __fadd_rn(tf, 1.0f);
-    if (l == 0) up = virt;
+    if (l == 0) up = tf;                               // free-start row: (a lower bound of) j*w in column j = t
+    tf = sqk_lb_virtual_next(tf, wt.w);
     const float y = lb_lds(raddr);
     raddr = lb_ring_next<16 * L * 4>(raddr);
     float dg = prev_up;
@@ -125,7 +124,8 @@ __device__ __forceinline__ unsigned lb_ring_next2(unsigned addr)
 
 // Two columns per step: this lane's K rows of columns j = t - 2l (cells A) and j + 1 (cells B).  B_k needs A_k, A_{k-1}
 // and B_{k-1}; A_k needs A_{k-1}: two dependency chains one cell apart, so the lane always has two independent
-// FMNMX3 -> FADD pairs in flight (the one-column step is latency-bound on a single chain).  tf == (float)t.
+// FMNMX3 -> FADD pairs in flight (the one-column step is latency-bound on a single chain).  tf: the free-start
+// row's value in column t.
 template <int K, int L, bool RAGGED>
 __device__ __forceinline__ void lb_step2(const float (&ci)[K], float (&co)[K], const float (&x)[K], unsigned &raddr, int l,
                                          bool pass0, int t, float &tf, float &bot_a, float &bot_b, float &prev_up_b,
@@ -133,10 +133,9 @@ __device__ __forceinline__ void lb_step2(const float (&ci)[K], float (&co)[K], c
 {
     float up_a = __shfl_up_sync(SQK_FULL_MASK, bot_a, 1, L);
     float up_b = __shfl_up_sync(SQK_FULL_MASK, bot_b, 1, L);
-    const float virt_a = sqk_lb_virtual(tf, wt.w);      // free-start row: j*w in column j (lane 0 is at columns t, t+1)
-    const float virt_b = sqk_lb_virtual(__fadd_rn(tf, 1.0f), wt.w);
-    tf = __fadd_rn(tf, 2.0f);
-    if (l == 0) { up_a = virt_a; up_b = virt_b; }
+    const float virt_b = sqk_lb_virtual_next(tf, wt.w); // free-start row: j*w in column j (lane 0 is at columns t, t+1)
+    if (l == 0) { up_a = tf; up_b = virt_b; }
+    tf = sqk_lb_virtual_next(virt_b, wt.w);
     const float2 y = lb_lds2(raddr);
     raddr = lb_ring_next2<16 * L * 4>(raddr);
     float dg_a = prev_up_b;                              // row above, column j-1
@@ -211,14 +210,15 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
     float c[K], c2[K];
     float bot = inf, bot_b = inf, prev_up = inf, tf = 0.0f;   // COLS == 2: bot is column A's bottom, prev_up is column B's
     LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.aeps = 0.0f; wt.bslack = 0.0f; wt.w = 0.0f; wt.n = 0; wt.N = a.N;
-    // groups of one warp start in phase and, with equal-length reads, stay in phase: rotate each group's ring by
-    // 8 banks per lane-group so that their simultaneous reads never share a bank
-    const int rot = (g * L) & (RC - 1);
+    // groups of one warp start in phase and, with equal-length reads, stay in phase: rotate each group's ring by the
+    // span its lanes read in one step so that simultaneous reads of different groups fall into different banks
+    const int rot = (g * L * COLS) & (RC - 1);
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     unsigned raddr = ring_s;
     int n = 0, t = 0, wcount = 0, my_read = -1, n_ref = 0;
     int64_t begin = 0, end = 0, cursor = 0, cursor0 = 0;
     double center = 0.0, scale = 1.0;
+    float inv_scale = 1.0f;
     bool done = true, exhausted = false;
 #pragma unroll
     for (int k = 0; k < K; k++) c[k] = inf;
@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         bot = inf; bot_b = inf;
                         prev_up = (l == 0) ? 0.0f : inf;
                         wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = n;
+                        inv_scale = sqk_lb_inv_scale(scale);
                         wt.w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
                         sqk_lb_slack(a.N, wt.w, &wt.aeps, &wt.bslack);
                         if (l == L - 1) lbc_reset(*cl);
@@ -312,8 +313,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     if (keep & (1u << e)) {
-                        const double y = __ddiv_rn(__dsub_rn((double)smp.get(e), center), scale);
-                        ring[(pos + rot) & (RC - 1)] = (float)y;   // round to nearest: |y - y32| <= 2^-24 |y|
+                        ring[(pos + rot) & (RC - 1)] = sqk_lb_y32((double)smp.get(e), center, inv_scale);
                         pos++;
                     }
                 }
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 
         // the cheap candidate test of this block of steps: U <= thr + (largest (j + N) * w of the block)
         if (l == L - 1 && !done) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + S + a.N), wt.w));
+        tf = sqk_lb_virtual((float)t, wt.w);          // free-start row at the block's first column; steps add w
         if constexpr (COLS == 2) {
 #pragma unroll 1
             for (int it = 0; it < S; it += 4) {

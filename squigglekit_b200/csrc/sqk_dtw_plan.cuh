@@ -111,12 +111,25 @@ SQK_HD float sqk_mul_rd(float a, float b) { return sqk_round_dir((double)a * (do
 SQK_HD float sqk_d2f_ru(double a) { return sqk_round_dir(a, 1); }
 #endif
 
-// Width of the local-cost deficit: |x - x32| + |y - y32| <= (|x| + |y|) * 2^-24 for round-to-nearest
-// conversions; the 2^-8 relative inflation also absorbs the float64 rounding of mlpy's own sums for paths of
-// up to 2^19 cells (SQK_LB_MAX_LEN + motif length).
+// The scan's float32 image of a normalised sample: (s - center) exactly as numpy computes it (one float64
+// rounding), narrowed to float32 and multiplied by the float32 image of 1/scale -- three roundings of 2^-24
+// relative each instead of a float64 division per sample.  |y - y32| <= 3.01 * 2^-24 * |y|.
+SQK_HD float sqk_lb_y32(double s, double center, float inv_scale32)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(__double2float_rn(__dsub_rn(s, center)), inv_scale32);
+#else
+    return (float)((double)(float)(s - center) * (double)inv_scale32);   // product of two floats is exact in double
+#endif
+}
+SQK_HD float sqk_lb_inv_scale(double scale) { return (float)(1.0 / scale); }
+
+// Width of the local-cost deficit: |x - x32| <= 2^-24 |x| (round-to-nearest conversion) and
+// |y - y32| <= 3.01 * 2^-24 |y| (sqk_lb_y32); the 2^-8 relative inflation also absorbs the float64 rounding of
+// mlpy's own sums for paths of up to 2^19 cells (SQK_LB_MAX_LEN + motif length).
 SQK_HD float sqk_lb_width(double xmax_abs, double ymax_abs)
 {
-    const double w = (xmax_abs + ymax_abs) * (1.0 / 16777216.0) * (1.0 + 1.0 / 256.0);
+    const double w = (xmax_abs + 3.01 * ymax_abs) * (1.0 / 16777216.0) * (1.0 + 1.0 / 256.0);
     return sqk_d2f_ru(w);
 }
 
@@ -136,8 +149,10 @@ SQK_HD float sqk_lb_cell(float x32, float y32, float m)
     return sqk_add_rd(fabsf(t), m);
 }
 
-// What the free-start row feeds into row 0 at column j (a lower bound of j*w), tj = (float)j exactly.
+// What the free-start row feeds into row 0 at column j: a lower bound of j*w.  Exact-ish at the first column of
+// every block of steps (tj = (float)j), advanced by rounded-down additions of w inside the block.
 SQK_HD float sqk_lb_virtual(float tj, float w) { return sqk_mul_rd(tj, w); }
+SQK_HD float sqk_lb_virtual_next(float v, float w) { return sqk_add_rd(v, w); }
 
 // L[j] from U[N-1][j]: subtract an upper bound of (j + N) * w.
 SQK_HD float sqk_lb_adjust(float u, int j, int N, float w)

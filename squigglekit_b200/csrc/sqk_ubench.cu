@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb(int step
     sqk_lb_slack(80, wt.w, &wt.aeps, &wt.bslack);
     unsigned raddr = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)((g * L - l) & (RC - 1));
     for (int t = 0; t < steps; t += 2) {
-        if ((t % (7 * L)) == 0 && l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 7 * L + 80), wt.w));
+        if ((t % (7 * L)) == 0) { if (l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 7 * L + 80), wt.w)); tf = sqk_lb_virtual((float)t, wt.w); }
         lb_step<K, L, false>(c, c2, x, raddr, l, false, t, tf, bot, prev_up, wt, cl, ck, t / 64, 0, 192);
         lb_step<K, L, false>(c2, c, x, raddr, l, false, t + 1, tf, bot, prev_up, wt, cl, ck, t / 64, 0, 192);
     }
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) ub_lb2(int ste
     sqk_lb_slack(80, wt.w, &wt.aeps, &wt.bslack);
     unsigned raddr = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)((g * L - 2 * l) & (RC - 1));
     for (int t = 0; t < steps; t += 4) {
-        if ((t % (6 * L)) == 0 && l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 6 * L + 80), wt.w));
+        if ((t % (6 * L)) == 0) { if (l == L - 1) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + 6 * L + 80), wt.w)); tf = sqk_lb_virtual((float)t, wt.w); }
         lb_step2<K, L, false>(c, c2, x, raddr, l, false, t, tf, bot_a, bot_b, prev_up_b, wt, cl, ck, t / 64, 0, 192);
         lb_step2<K, L, false>(c2, c, x, raddr, l, false, t + 2, tf, bot_a, bot_b, prev_up_b, wt, cl, ck, t / 64, 0, 192);
     }

@@ -54,11 +54,11 @@ Hit exact_window(const double *x, int N, const double *y, int col0, int n_cols, 
 
 extern "C" {
 
-// y: normalised kept samples (float64) of one read, n of them; keep[raw_len]: 1 where the raw sample survived the
+// y: normalised kept samples (float64) of one read, sv: the same samples before normalisation, n of them; keep[raw_len]: 1 where the raw sample survived the
 // outlier filter (sum == n); align_off: raw samples between the aligned block start and the read's first sample;
 // ch: raw samples per refill (8 * lanes).  out: start, end; *dist.  diag[0..7]: n_clusters, n_jobs, fallback
 // (0 proven, 1 fallback), flags, lower-bound violations (must be 0), tainted windows, window columns, max L gap *1e9.
-int plan_two_pass(const double *x, int N, const double *y, int n, const uint8_t *keep, int raw_len, int align_off, int ch,
+int plan_two_pass(const double *x, int N, const double *y, const double *sv, int n, const uint8_t *keep, int raw_len, int align_off, int ch,
                   int lo, int hi, double center, double scale, int W, int32_t *out, double *dist, int64_t *diag)
 {
     const float inf = std::numeric_limits<float>::infinity();
@@ -96,8 +96,9 @@ int plan_two_pass(const double *x, int N, const double *y, int n, const uint8_t 
         // the lane that owns the last row sees column j at step t = j + lanes - 1; blocks of S steps share one thr_u
         const int t = j - j % cols + LAG;
         if (j == 0 || (t % S == 0 && j % cols == 0)) thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(t - t % S + S + N), w));
-        const float y32 = (float)y[j];
-        const float virt = sqk_lb_virtual((float)j, w);
+        const float y32 = sqk_lb_y32(sv[j], center, sqk_lb_inv_scale(scale));
+        // free-start row: exact-ish at the first column of each block (lane 0's clock is the column), += w inside
+        const float virt = (j % S == 0) ? sqk_lb_virtual((float)j, w) : sqk_lb_virtual_next(prev_virt, w);
         for (int i = 0; i < N; i++) {
             float m;
             if (i == 0) m = std::fmin(std::fmin(virt, prev_virt), j == 0 ? inf : c[0]);   // free-start row: j*w, (j-1)*w, left

@@ -26,7 +26,7 @@ def harness(tmp_path_factory):
                            os.path.join(ROOT, "tests", "plan_harness.cpp"), "-o", out])
     lib = C.CDLL(out)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-    lib.plan_two_pass.argtypes = [dp, C.c_int, dp, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    lib.plan_two_pass.argtypes = [dp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, ip, dp, C.POINTER(C.c_int64)]
     lib.plan_exact.argtypes = [dp, C.c_int, dp, C.c_int, ip, dp]
     return lib
@@ -44,14 +44,15 @@ def _prep(sig, lo, hi, scale):
     else:
         center, sc = 0.0, 1.0
     y = (kept - center) / sc
-    return np.ascontiguousarray(y), keep.astype(np.uint8), float(center), float(sc)
+    return np.ascontiguousarray(y), np.ascontiguousarray(kept), keep.astype(np.uint8), float(center), float(sc)
 
 
 def _run(lib, motif, sig, lo=0, hi=1200, scale="zscale", W=0, lanes=8, align_off=0):
-    y, keep, center, sc = _prep(sig, lo, hi, scale)
+    y, kept, keep, center, sc = _prep(sig, lo, hi, scale)
     x = np.ascontiguousarray(motif, dtype=np.float64)
     out = np.zeros(2, np.int32); dist = C.c_double(); diag = np.zeros(8, np.int64)
-    rc = lib.plan_two_pass(x.ctypes.data_as(C.POINTER(C.c_double)), x.size, y.ctypes.data_as(C.POINTER(C.c_double)), y.size,
+    rc = lib.plan_two_pass(x.ctypes.data_as(C.POINTER(C.c_double)), x.size, y.ctypes.data_as(C.POINTER(C.c_double)),
+                           kept.ctypes.data_as(C.POINTER(C.c_double)), y.size,
                            keep.ctypes.data_as(C.POINTER(C.c_uint8)), keep.size, align_off, 8 * lanes, lo, hi, center, sc, W,
                            out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(dist), diag.ctypes.data_as(C.POINTER(C.c_int64)))
     assert rc == 0, f"harness rc {rc}"
