@@ -157,6 +157,33 @@ SQK_API int sqk_segmenter_pa(sqk_ctx *ctx, const int16_t *signals, const int64_t
                              const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
 
 /* ---------------------------------------------------------------------------------------
+ * dRNA adapter finder -- the slow5 branch of dRNA_segmenter.py (dRNA_segmenter.py:86-176).  Per read:
+ *     sig = scale_outliers(signal)                    keep 0 < s < 1200              :88, :331-334
+ *     median, stdev of sig[t_start:t_end]; top = median + stdev * 0.8               :104-106
+ *     one-sided run detector  a < top  with the constants of :89-100                 :108-166
+ *     print the first segment                                                        :171-174
+ * The reference hard-codes every constant; they are parameters here with those defaults
+ * (SQK_ADAPTER_DEFAULTS).  segs: [n_reads][2] int32 (start, end) in post-outlier coordinates; found[n_reads]:
+ * 1 = a segment was found, 0 = none (the reference prints nothing), -1 = read longer than the declared
+ * max_read_len.  (The TSV branch of that script, :272-326, cannot run as shipped -- `w` is undefined -- and is
+ * not provided.)
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t error;          /* 5    :90  */
+    int32_t no_err_thresh;  /* 2500 :91  tolerated samples count as errors only from this position on */
+    int32_t corrector;      /* 1200 :96  (w) */
+    int32_t window;         /* 100  :97  */
+    int32_t seg_dist;       /* 1200 :99  */
+    int32_t t_start, t_end; /* 1000, 5000 :82-83: the slice the threshold statistics come from */
+    double std_scale;       /* 0.8  :106 */
+    int32_t lim_lo, lim_hi; /* 0, 1200 :333 */
+} sqk_adapter_params;
+#define SQK_ADAPTER_DEFAULTS {5, 2500, 1200, 100, 1200, 1000, 5000, 0.8, 0, 1200}
+
+SQK_API int sqk_adapter(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                        int64_t max_read_len, const sqk_adapter_params *params, int mem, int32_t *segs, int32_t *found);
+
+/* ---------------------------------------------------------------------------------------
  * float64 signals.  The reference's `-s` path hands both tools whatever the TSV holds (MotifSeq.py:270
  * `float(i) for i in l[8:]`; segmenter.py:198-199), e.g. SquigglePull's pA output.  Same semantics and outputs as
  * sqk_motifseq / sqk_segmenter with `signals` as float64: outlier window, numpy-exact float statistics (pairwise

@@ -6,6 +6,7 @@ There is no CPU fallback: importing the package is cheap, using it needs the bui
 B200.
 """
 from .core import (  # noqa: F401
+    AdapterConfig,
     Context,
     SegConfig,
     SqkError,

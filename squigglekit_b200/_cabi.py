@@ -40,6 +40,12 @@ class SegParams(C.Structure):
                 ("num", C.c_int32), ("max_segs", C.c_int32)]
 
 
+class AdapterParams(C.Structure):
+    _fields_ = [("error", C.c_int32), ("no_err_thresh", C.c_int32), ("corrector", C.c_int32), ("window", C.c_int32),
+                ("seg_dist", C.c_int32), ("t_start", C.c_int32), ("t_end", C.c_int32), ("std_scale", C.c_double),
+                ("lim_lo", C.c_int32), ("lim_hi", C.c_int32)]
+
+
 class Timing(C.Structure):
     _fields_ = [("launches", C.c_int64 * K_COUNT), ("ms", C.c_double * K_COUNT)]
 
@@ -47,7 +53,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sqk_version", "sqk_last_error", "sqk_ctx_create", "sqk_ctx_destroy", "sqk_ctx_set_stream", "sqk_ctx_sync",
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
-    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
+    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
 ]
 
 _lib = None
@@ -77,6 +83,7 @@ def lib() -> C.CDLL:
     L.sqk_motifseq.argtypes = [vp, vp, vp, i64, i64, vp, vp, i32, C.POINTER(MotifParams), C.c_int, vp, vp]
     L.sqk_motifseq_trace.argtypes = [vp, vp, i64, vp, i32, C.POINTER(MotifParams), vp, vp, i64, C.POINTER(i64), vp]
     L.sqk_segmenter.argtypes = [vp, vp, vp, i64, i64, C.POINTER(SegParams), C.c_int, vp, vp]
+    L.sqk_adapter.argtypes = [vp, vp, vp, i64, i64, C.POINTER(AdapterParams), C.c_int, vp, vp]
     L.sqk_segmenter_pa.argtypes = [vp, vp, vp, i64, i64, vp, vp, C.POINTER(SegParams), C.c_int, vp, vp]
     L.sqk_motifseq_f64.argtypes = [vp, vp, vp, i64, vp, vp, i32, C.POINTER(MotifParams), C.c_int, vp, vp]
     L.sqk_segmenter_f64.argtypes = [vp, vp, vp, i64, C.POINTER(SegParams), C.c_int, vp, vp]

@@ -42,6 +42,21 @@ class SegConfig:
     max_segs: int = 16
 
 
+@dataclass
+class AdapterConfig:
+    """The constants the slow5 branch of dRNA_segmenter.py hard-codes (dRNA_segmenter.py:82-106, :333)."""
+    error: int = 5
+    no_err_thresh: int = 2500
+    corrector: int = 1200
+    window: int = 100
+    seg_dist: int = 1200
+    t_start: int = 1000
+    t_end: int = 5000
+    std_scale: float = 0.8
+    lim_low: int = 0
+    lim_hi: int = 1200
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -285,6 +300,37 @@ class Context:
             _cabi.check(self._lib.sqk_segmenter(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
                                                 C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, nsegs.ctypes.data))
         return segs, nsegs
+
+
+def _adapter(self, signals, offsets, cfg: AdapterConfig = AdapterConfig(), max_read_len: int = 0):
+    """Batched dRNA adapter finder (dRNA_segmenter.py:86-176, slow5 branch): per read scale_outliers, threshold
+    from kept samples [t_start, t_end), one-sided run detector, first segment.
+
+    -> (segs int32 [n_reads, 2], found int32 [n_reads]); found == 0: the reference prints nothing for that read."""
+    p = _cabi.AdapterParams(cfg.error, cfg.no_err_thresh, cfg.corrector, cfg.window, cfg.seg_dist, cfg.t_start, cfg.t_end,
+                            cfg.std_scale, cfg.lim_low, cfg.lim_hi)
+    if _is_torch(signals):
+        import torch
+        if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
+            raise TypeError("device mode needs int16 signals and int64 offsets")
+        n_reads = offsets.numel() - 1
+        segs = torch.zeros((n_reads, 2), dtype=torch.int32, device=signals.device)
+        found = torch.zeros(n_reads, dtype=torch.int32, device=signals.device)
+        self._use_torch_stream()
+        _cabi.check(self._lib.sqk_adapter(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, int(max_read_len),
+                                          C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(), found.data_ptr()))
+        return segs, found
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n_reads = offsets.size - 1
+    segs = np.zeros((n_reads, 2), dtype=np.int32)
+    found = np.zeros(n_reads, dtype=np.int32)
+    _cabi.check(self._lib.sqk_adapter(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
+                                      C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, found.ctypes.data))
+    return segs, found
+
+
+Context.adapter = _adapter
 
 
 def hits_from_torch(hits_u8) -> np.ndarray:

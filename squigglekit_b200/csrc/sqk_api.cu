@@ -15,6 +15,7 @@
 #include "sqk_dtw_launch.cuh"
 #include "sqk_dtw_lb.cuh"
 #include "sqk_segmenter.cuh"
+#include "sqk_adapter.cuh"
 #include "sqk_f64.cuh"
 #include "sqk_stats.cuh"
 
@@ -343,7 +344,7 @@ static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, c
 
 static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
                         double std_scale, int32_t *d_nkept, const double *d_pa_off = nullptr,
-                        const double *d_pa_scale = nullptr)
+                        const double *d_pa_scale = nullptr, int t_start = 0, int t_end = 0)
 {
     lo = clamp_lim(lo); hi = clamp_lim(hi);
     TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
@@ -353,6 +354,7 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     a.stats = (ReadStats *)s.stats.p; a.n_kept_out = d_nkept;
     a.mode = mode; a.lo = lo; a.hi = hi; a.num = num; a.std_scale = std_scale;
     a.pa_offset = d_pa_off; a.pa_scale = d_pa_scale;
+    a.t_start = t_start; a.t_end = t_end;
     // one CTA per read; the warp-per-read form (SQK_STATS_NT=32, reads <= 8192 samples) is kept for experiments
     static int force_nt = -1;
     if (force_nt < 0) { const char *e = getenv("SQK_STATS_NT"); force_nt = e ? atoi(e) : 0; }
@@ -572,6 +574,39 @@ static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v
     cudaEvent_t eb;
     TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
     sqk_fsm_kernel<<<grid, SQK_FSM_THREADS, 0, st>>>(a);
+    CU(cudaGetLastError());
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+static int check_adapter_params(const sqk_adapter_params *p)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    if (p->corrector < 1) return fail(SQK_ERR_ARG, "corrector must be >= 1");
+    if (p->window < 0 || p->error < 0) return fail(SQK_ERR_ARG, "window and error must be >= 0");
+    if (p->t_start < 0 || p->t_end < 0) return fail(SQK_ERR_ARG, "t_start and t_end must be >= 0");
+    return SQK_OK;
+}
+
+// dRNA adapter finder: statistics of kept samples [t_start, t_end) (K1, SQK_STATS_ADAPTER) + its state machine
+static int enqueue_adapter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const sqk_adapter_params *p,
+                           int32_t *d_segs, int32_t *d_found)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    TRY(launch_stats(c, s, st, v, SQK_STATS_ADAPTER, p->lim_lo, p->lim_hi, 0, p->std_scale, nullptr, nullptr, nullptr,
+                     p->t_start, p->t_end));
+    AdapterArgs a{};
+    a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+    a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+    a.stats = (const ReadStats *)s.stats.p;
+    a.error = p->error; a.no_err_thresh = p->no_err_thresh; a.corrector = p->corrector; a.window = p->window;
+    a.seg_dist = p->seg_dist;
+    a.segs = d_segs; a.found = d_found;
+    const unsigned grid = (unsigned)((v.n_reads + SQK_ADAPTER_THREADS - 1) / SQK_ADAPTER_THREADS);
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
+    sqk_adapter_fsm_kernel<<<grid, SQK_ADAPTER_THREADS, 0, st>>>(a);
     CU(cudaGetLastError());
     TRY(tock(eb, st));
     return SQK_OK;
@@ -972,7 +1007,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
 
 static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
                           const double *pa_offset, const double *pa_scale, const sqk_seg_params *p, int mem, int32_t *segs,
-                          int32_t *n_segs)
+                          int32_t *n_segs, const sqk_adapter_params *ap = nullptr)
 {
     if ((pa_offset == nullptr) != (pa_scale == nullptr)) return fail(SQK_ERR_ARG, "pa_offset and pa_scale must be given together");
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
@@ -980,17 +1015,19 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     if (n_reads == 0) return SQK_OK;
     if (!offsets || !segs || !n_segs) return fail(SQK_ERR_ARG, "offsets/segs/n_segs is NULL");
     if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
-    TRY(check_seg_params(p));
+    if (ap) TRY(check_adapter_params(ap));      // adapter mode: one (start, end) row per read, n_segs = found flag
+    else TRY(check_seg_params(p));
     Guard g(c->device);
     if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
-    const size_t seg_row = (size_t)p->max_segs * 2 * sizeof(int32_t);
+    const size_t seg_row = (size_t)(ap ? 1 : p->max_segs) * 2 * sizeof(int32_t);
 
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
         if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
-        TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale));
+        if (ap) TRY(enqueue_adapter(c, c->slot[0], st, v, ap, segs, n_segs));
+        else TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale));
         return SQK_OK;
     }
 
@@ -1027,7 +1064,8 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
             d_po = (const double *)s.pa_off.p - r0; d_ps = (const double *)s.pa_scale.p - r0;
         }
         View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
-        TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p, d_po, d_ps));
+        if (ap) TRY(enqueue_adapter(c, s, st, v, ap, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
+        else TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p, d_po, d_ps));
         TRY(result_to_host(s, 0, (char *)segs + (size_t)r0 * seg_row, s.segs.p, (size_t)nr * seg_row, segs_pinned));
         TRY(result_to_host(s, 1, n_segs + r0, s.nsegs.p, (size_t)nr * sizeof(int32_t), nsegs_pinned));
     }
@@ -1148,6 +1186,13 @@ int sqk_segmenter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, in
                   const sqk_seg_params *p, int mem, int32_t *segs, int32_t *n_segs)
 {
     return segmenter_impl(c, signals, offsets, n_reads, max_read_len, nullptr, nullptr, p, mem, segs, n_segs);
+}
+
+int sqk_adapter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                const sqk_adapter_params *p, int mem, int32_t *segs, int32_t *found)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    return segmenter_impl(c, signals, offsets, n_reads, max_read_len, nullptr, nullptr, nullptr, mem, segs, found, p);
 }
 
 int sqk_segmenter_pa(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,

@@ -23,6 +23,9 @@
 //             The state machine itself is K3 (sqk_segmenter.cuh).  (A variant that ran get_segs here, on a bit
 //             mask of the staged samples with popc run-skipping, was measured and dropped: one thread per read
 //             walking ~300 candidate segments is slower than K3's 32 reads per warp.)
+//   adapter   dRNA_segmenter.py:104-106: median and sd of the post-outlier samples [t_start, t_end) only,
+//             top = median + sd*std_scale, in range <=> x < top -> seg_hi = ceil(top)-1 (sqk_adapter.cuh has the
+//             state machine).
 #pragma once
 #include "sqk_common.cuh"
 
@@ -33,7 +36,7 @@
 #define SQK_HEAP_NODES 256          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
 #define SQK_HEAP_MAX_N 8192
 
-enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3 };
+enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3, SQK_STATS_ADAPTER = 4 };
 
 struct StatsArgs {
     const int16_t *base;      // base[i] = absolute sample i
@@ -43,6 +46,7 @@ struct StatsArgs {
     ReadStats *stats;         // [n_reads], launch-local index
     int32_t *n_kept_out;      // [n_reads] or null
     int mode, lo, hi, num;
+    int t_start, t_end;       // SQK_STATS_ADAPTER: the statistics come from kept samples [t_start, t_end) only
     double std_scale;
     const double *pa_offset;  // segmenter pA mode: per-read calibration, indexable by absolute read id (or null)
     const double *pa_scale;   //   pA = round((d + pa_offset) * pa_scale, 2)
@@ -556,6 +560,54 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS, 6) sqk_stats_kernel(const S
                     out.seg_lo = (bot == bot) ? stats_first_above(bot, pa_off, pa_unit) : 40000;
                 }
                 out.center = top; out.scale = bot;
+            }
+        }
+
+        if (a.mode == SQK_STATS_ADAPTER) {
+            // python slice sig[t_start:t_end] of the post-outlier signal; an empty slice gives NaN statistics
+            int s0 = a.t_start < n ? a.t_start : n, s1 = a.t_end < n ? a.t_end : n;
+            if (s0 < 0) s0 = 0;
+            if (s1 < s0) s1 = s0;
+            const int ns = s1 - s0;
+            out.seg_lo = -40000; out.seg_hi = -40001;            // nothing is in range
+            out.center = __longlong_as_double(0x7ff8000000000000LL); out.scale = out.center;
+            if (ns > 0) {
+                const int16_t *sl = stage + s0;
+                long long part = 0;
+                for (int q = tid; q < ns; q += NT) part += sl[q];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SQK_FULL_MASK, part, d);
+                long long slice_sum = part;
+                if (NT > 32) {
+                    stats_sync<NT>();
+                    if (lane == 0) sh.sum_part[warp] = (unsigned long long)part;
+                    stats_sync<NT>();
+                    slice_sum = 0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++) slice_sum += (long long)sh.sum_part[w];
+                    stats_sync<NT>();
+                }
+                const double mean = __ddiv_rn((double)slice_sum, (double)ns);
+                auto sq = [sl, mean](int q) -> double { const double d = __dsub_rn((double)sl[q], mean); return __dmul_rn(d, d); };
+                const double sdev = __dsqrt_rn(__ddiv_rn(stats_sum<NT>(sq, ns, sh), (double)ns));
+                const int nbins = out_hi - out_lo + 1;
+                auto key_x = [sl](int q) -> uint32_t { return (uint32_t)((int)sl[q] + 32768); };
+                int lo_v, hi_v;
+                if (nbins <= SQK_HIST_BINS) {
+                    stats_histogram<NT>(sl, ns, out_lo, sh);
+                    lo_v = out_lo + stats_hist_select(sh, nbins, (ns - 1) / 2);
+                    hi_v = (ns & 1) ? lo_v : out_lo + stats_hist_select(sh, nbins, ns / 2);
+                } else if (ns & 1) {
+                    lo_v = hi_v = (int)stats_select<NT>(key_x, ns, (ns - 1) / 2, sh) - 32768;
+                } else {
+                    lo_v = (int)stats_select<NT>(key_x, ns, ns / 2 - 1, sh) - 32768;
+                    hi_v = (int)stats_select<NT>(key_x, ns, ns / 2, sh) - 32768;
+                }
+                const double median = (double)(lo_v + hi_v) * 0.5;
+                const double top = __dadd_rn(median, __dmul_rn(sdev, a.std_scale));
+                // integer x:  x < top  <=>  x <= ceil(top)-1
+                if (top == top) out.seg_hi = (int)fmin(fmax(ceil(top) - 1.0, -40000.0), 40000.0);
+                out.center = top; out.scale = median;
             }
         }
 

@@ -161,3 +161,15 @@ def test_pa_conversion_matches_numpy_round():
     for offset, rg, dig in ((16.0, 1493.94, 8192.0), (-7.0, 1234.56, 8192.0), (3.0, 1467.61, 2048.0)):
         want = np.round((raw.astype(int) + offset) * (rg / dig), 2)
         assert np.array_equal(oracle.convert_to_pa(raw, offset, rg / dig), want)
+
+
+def test_adapter_oracle_matches_reference_loop(golden_dir):
+    """dRNA_segmenter.py's slow5-branch loop (run from the reference file by tests/golden/make_adapter_golden.py)
+    vs the C restatement, on the committed vectors: the reference's example BLOW5 read + synthetic dRNA-like reads."""
+    import json
+    g = np.load(os.path.join(golden_dir, "adapter_inputs.npz"))
+    want = json.load(open(os.path.join(golden_dir, "adapter_golden.json")))["segments"]
+    segs, found = oracle.adapter_batch(g["signals"], g["offsets"])
+    got = [[int(segs[r, 0]), int(segs[r, 1])] if found[r] else None for r in range(len(want))]
+    assert got == want
+    assert sum(w is not None for w in want) >= 30 and any(w is None for w in want)
