@@ -338,12 +338,13 @@ def main():
         achieved = R * BYTES_PER_READ / (dtw_ms * 1e-3) / 1e9
         alu_peak, alu_src = alu_peak_cells_per_s(ub, ubp)
         cells_s = R * CELLS_PER_READ / (dtw_ms * 1e-3)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "dtw_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch_100k_reads_lb" if two_pass else "dram_bytes_per_launch_100k_reads")
-        except Exception:
-            pass
+        traffic = None      # ncu dram__bytes_read + dram__bytes_write of one launch: only known for the captured shape
+        if R == 100000 and M == 4096 and N_MOTIF == 80:
+            try:
+                with open(os.path.join(ROOT, "profiles", "dtw_traffic.json")) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch_100k_reads_lb" if two_pass else "dram_bytes_per_launch_100k_reads")
+            except Exception:
+                pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sub_n = 8192
