@@ -11,9 +11,10 @@
 //
 //   zscale    mean = sum/n (integer sum: exact, order-free);  sd = sqrt(S/n) with S = the sum of
 //             fl(fl(x-mean)^2) taken in numpy's pairwise order: 8-lane teams own the <=128-element
-//             leaves (one lane per strided accumulator, xor-butterfly = numpy's fold); subtrees of <= 8192
-//             elements are built and folded level by level at heap indices, the levels above them are walked
-//             depth-first -> same bits as sklearn.preprocessing.scale / np.std.
+//             leaves (one lane per strided accumulator, xor-butterfly = numpy's fold); each team finds its leaf by
+//             walking the split rule down from the root, one warp folds the leaf sums of a subtree of <= 8192
+//             elements in slot order, the levels above such subtrees are walked depth-first
+//             -> same bits as sklearn.preprocessing.scale / np.std.
 //   medmad    median and MAD from ONE shared-memory histogram of the raw values + prefix scan when the
 //             outlier window spans <= 2048 values (MAD by binary search on count(|2v - 2med| <= D)),
 //             else by two-pass radix select: exact, including the x.5 medians of even-length reads.
@@ -33,7 +34,7 @@
 #define SQK_TREE_DEPTH 24
 #define SQK_HIST_BINS 2048          // direct histogram when the outlier window spans <= 2048 raw values
 #define SQK_RADIX_BINS 512          // fallback two-pass radix select (9 + 8 bits)
-#define SQK_HEAP_NODES 256          // parallel pairwise tree for n <= SQK_HEAP_MAX_N (heap-indexed nodes)
+#define SQK_TREE_SLOTS 128          // leaf slots of the parallel pairwise tree: depth <= 7 for n <= SQK_HEAP_MAX_N
 #define SQK_HEAP_MAX_N 8192
 
 enum { SQK_STATS_ZSCALE = 0, SQK_STATS_MEDMAD = 1, SQK_STATS_NONE = 2, SQK_STATS_SEGMENTER = 3, SQK_STATS_ADAPTER = 4 };
@@ -58,13 +59,12 @@ struct StatsArgs {
 struct StatsShared {
     union {                                           // the two users never overlap in time
         uint32_t hist[SQK_HIST_BINS + SQK_HIST_BINS / 32];   // median / MAD histogram, then its prefix sums (padded, see HB)
-        struct {
-            int off[SQK_HEAP_NODES], len[SQK_HEAP_NODES];
-            double sum[SQK_HEAP_NODES];
-        } hp;                                         // heap-indexed pairwise tree (n <= SQK_HEAP_MAX_N)
+        double leaf[SQK_TREE_SLOTS];                  // leaf sums of the pairwise tree (n <= SQK_HEAP_MAX_N), in slot order
     };
+    double tree_out;
     unsigned long long sum_part[4];
     int warp_tot[4];
+    int scan_tot[2][4][4];                            // compaction pass: [iteration parity][block of the thread][warp]
     uint32_t scan_part[4];
     uint32_t sel[2];
 };
@@ -99,60 +99,57 @@ __device__ __forceinline__ double stats_leaf_sum(Term term, int off, int len, in
     return r;
 }
 
-// Same sum, tree built and folded in parallel: nodes live at heap indices (root 1, children 2h and 2h+1),
-// one level per barrier on the way down (split) and up (left + right).  n <= SQK_HEAP_MAX_N: depth <= 7.
+// Same sum for n <= SQK_HEAP_MAX_N with two barriers.  numpy's split rule (left half = floor(len/2) rounded down to a
+// multiple of 8) is a pure function of n, so every 8-lane team finds the leaf of slot j on its own by walking j's bits
+// down from the root -- no tree is built in memory.  The right child is never the smaller one, so the depth of the
+// right-most path is the depth D of the tree; a node that drops to <= 128 elements above level D is a leaf whose sum is
+// stored in the slot of its left-most descendant, the other descendant slots hold 0.0 (x + 0.0 == x exactly).  One warp
+// then folds the 2^D slots pairwise in slot order, which is exactly the order in which numpy adds the halves.
 template <int NT, class Term>
 __device__ double stats_pairwise_heap(Term term, int n, StatsShared &sh)
 {
     const int tid = threadIdx.x % NT;
     constexpr int TEAMS = NT / 8;
-    for (int h = tid; h < SQK_HEAP_NODES; h += NT) sh.hp.len[h] = 0;
-    stats_sync<NT>();
-    if (tid == 0) { sh.hp.off[1] = 0; sh.hp.len[1] = n; }
-    stats_sync<NT>();
-    int depth = 0;          // deepest level that holds nodes
-    for (int d = 0; (4 << d) <= SQK_HEAP_NODES; d++) {
-        int split = 0;
-        for (int h = (1 << d) + tid; h < (2 << d); h += NT) {
-            const int len = sh.hp.len[h];
-            if (len > 128) {
-                const int off = sh.hp.off[h];
-                int half = len / 2;
-                half -= half % 8;
-                sh.hp.off[2 * h] = off; sh.hp.len[2 * h] = half;
-                sh.hp.off[2 * h + 1] = off + half; sh.hp.len[2 * h + 1] = len - half;
-                split = 1;
-            }
-        }
-        if (!stats_sync_or<NT>(split)) break;
-        depth = d + 1;
-    }
-    // leaves: nodes with 0 < len <= 128 (they sit on the last two levels); 8-lane teams, warps stay converged
+    int depth = 0;
+    for (int len = n; len > 128; depth++) { int half = len / 2; half -= half % 8; len -= half; }
+    const int slots = 1 << depth;                      // <= SQK_TREE_SLOTS
     const int team = tid >> 3, k = tid & 7;
-    const int first = depth > 0 ? (1 << (depth - 1)) : 1, last = (2 << depth);
-    for (int h0 = first; h0 < last; h0 += TEAMS) {
-        const int h = h0 + team;
-        const int len = h < last ? sh.hp.len[h] : 0;
-        const bool leaf = len > 0 && len <= 128;
-        // every team runs the shuffles; non-leaves sum a dummy leaf at offset 0
-        const int use_off = leaf ? sh.hp.off[h] : 0;
-        const int use_len = leaf ? len : (n >= 8 ? 8 : n);
-        const double v = stats_leaf_sum(term, use_off, use_len, k);
-        if (leaf && k == 0) sh.hp.sum[h] = v;
+    for (int j0 = 0; j0 < slots; j0 += TEAMS) {
+        const int j = j0 + team;
+        int off = 0, len = n, d = 0;
+        bool mine = j < slots;
+        // walk down: bit (depth-1-d) of j picks the child at level d
+        while (len > 128) {
+            int half = len / 2; half -= half % 8;
+            if ((j >> (depth - 1 - d)) & 1) { off += half; len -= half; } else len = half;
+            d++;
+        }
+        // an early leaf (d < depth) belongs to the slot whose remaining bits are all zero
+        if (mine && d < depth && (j & ((1 << (depth - d)) - 1)) != 0) mine = false;
+        // every team runs the shuffles; teams without a leaf sum a dummy one at offset 0
+        const double v = stats_leaf_sum(term, mine ? off : 0, mine ? len : (n >= 8 ? 8 : n), k);
+        if (j < slots && k == 0) sh.leaf[j] = mine ? v : 0.0;
     }
     stats_sync<NT>();
-    for (int d = depth - 1; d >= 0; d--) {
-        for (int h = (1 << d) + tid; h < (2 << d); h += NT)
-            if (sh.hp.len[h] > 128) sh.hp.sum[h] = __dadd_rn(sh.hp.sum[2 * h], sh.hp.sum[2 * h + 1]);
-        stats_sync<NT>();
+    if (tid < 32) {
+        // 2^depth slots -> one warp: lane i folds its run of consecutive slots pairwise, then the lanes fold pairwise
+        const int per = slots > 32 ? slots / 32 : 1;   // 1, 2 or 4
+        double r;
+        if (per == 1) r = tid < slots ? sh.leaf[tid] : 0.0;
+        else if (per == 2) r = __dadd_rn(sh.leaf[2 * tid], sh.leaf[2 * tid + 1]);
+        else r = __dadd_rn(__dadd_rn(sh.leaf[4 * tid], sh.leaf[4 * tid + 1]), __dadd_rn(sh.leaf[4 * tid + 2], sh.leaf[4 * tid + 3]));
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) r = __dadd_rn(r, shfl_xor_f64(r, m, 32));
+        if (tid == 0) sh.tree_out = r;
     }
-    const double r = sh.hp.sum[1];
+    stats_sync<NT>();
+    const double r = sh.tree_out;
     stats_sync<NT>();
     return r;
 }
 
 // np.sum over term(0..n-1) in numpy's pairwise order, any n.  numpy's recursion applies the same rule to every
-// subtree, so each subtree of <= SQK_HEAP_MAX_N elements is summed by the parallel heap routine and the few levels
+// subtree, so each subtree of <= SQK_HEAP_MAX_N elements is summed by the parallel routine above and the few levels
 // above are walked depth-first and folded with a depth stack -- identically in every thread of the group (the
 // control flow depends on n only), so the collective calls inside stay converged.
 template <int NT, class Term>
@@ -387,80 +384,92 @@ __global__ void __launch_bounds__(SQK_STATS_THREADS, 6) sqk_stats_kernel(const S
         const unsigned span = (unsigned)(out_hi - out_lo);
         const int64_t blk0 = aligned_block_start(a.base, begin);
         constexpr int U = 4;                      // 16-byte loads in flight per thread
-        for (int64_t cb = blk0; cb < end; cb += (int64_t)NT * 8 * U) {
+        int parity = 0;
+        for (int64_t cb = blk0; cb < end; cb += (int64_t)NT * 8 * U, parity ^= 1) {
+            // Block b = u*NT + tid of this iteration holds samples cb + 8b .. +8; compacted positions follow block order.
             Samples8 sv[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int64_t blk = cb + ((int64_t)u * NT + tid) * 8;
                 if (blk < end && blk + 8 > begin) sv[u] = load_block8(a.base, blk, alloc_lo, alloc_hi);
             }
+            unsigned keep[U];
+            int incl[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int64_t blk = cb + ((int64_t)u * NT + tid) * 8;
-                if (cb + (int64_t)u * NT * 8 >= end) break;           // uniform over the group
                 const Samples8 s = sv[u];
-                unsigned keep = 0;
+                keep[u] = 0;
                 if (blk < end && blk + 8 > begin) {
                     // one unsigned compare per sample for the window; edge blocks mask the samples outside the read
                     int lsum = 0;
+                    unsigned kp = 0;
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         const int v = s.get(e);
-                        if ((unsigned)(v - out_lo) <= span) { keep |= 1u << e; lsum += v; }
+                        if ((unsigned)(v - out_lo) <= span) { kp |= 1u << e; lsum += v; }
                     }
                     if (blk < begin || blk + 8 > end) {
                         const int first = blk < begin ? (int)(begin - blk) : 0;
                         const int last = blk + 8 > end ? (int)(end - blk) : 8;          // valid samples: [first, last)
                         const unsigned valid = ((1u << last) - 1u) & ~((1u << first) - 1u);
-                        const unsigned drop = keep & ~valid;
-                        keep &= valid;
+                        const unsigned drop = kp & ~valid;
+                        kp &= valid;
 #pragma unroll
                         for (int e = 0; e < 8; e++)
                             if (drop & (1u << e)) lsum -= s.get(e);
                     }
-                    if (!window_ok) { keep = 0; lsum = 0; }
+                    if (!window_ok) { kp = 0; lsum = 0; }
                     sum += lsum;
+                    keep[u] = kp;
                 }
-                const int cnt = __popc(keep);
-                int incl = cnt;
+                // inclusive scan of the kept counts over the warp, one per block row u
+                int inc = __popc(keep[u]);
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(SQK_FULL_MASK, incl, d);
-                    if (lane >= d) incl += t;
+                    const int t = __shfl_up_sync(SQK_FULL_MASK, inc, d);
+                    if (lane >= d) inc += t;
                 }
-                int pos = total + incl - cnt, all;
+                incl[u] = inc;
+                if (NT > 32 && lane == 31) sh.scan_tot[parity][u][warp] = inc;
+            }
+            // ONE barrier per iteration: the warp totals of all U block rows become visible together (the buffer
+            // alternates with the iteration, so the next iteration's writes cannot overtake this iteration's reads)
+            if (NT > 32) __syncthreads();
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                int pos = total + incl[u] - __popc(keep[u]), all;
                 if (NT == 32) {
-                    all = __shfl_sync(SQK_FULL_MASK, incl, 31);
+                    all = __shfl_sync(SQK_FULL_MASK, incl[u], 31);
                 } else {
-                    if (lane == 31) sh.warp_tot[warp] = incl;
-                    __syncthreads();
                     all = 0;
 #pragma unroll
                     for (int w = 0; w < WARPS; w++) {
-                        const int t = sh.warp_tot[w];
+                        const int t = sh.scan_tot[parity][u][w];
                         if (w < warp) pos += t;
                         all += t;
                     }
                 }
-                if (staged && keep) {
+                const unsigned kp = keep[u];
+                const Samples8 s = sv[u];
+                if (staged && kp) {
                     if (in_smem) {
                         // shared-memory window: a fully kept block landing on an even position goes out as four words
-                        if (keep == 0xffu && !(pos & 1)) {
+                        if (kp == 0xffu && !(pos & 1)) {
                             uint32_t *w32 = reinterpret_cast<uint32_t *>(smem_stage + pos);
                             w32[0] = (uint32_t)s.v.x; w32[1] = (uint32_t)s.v.y; w32[2] = (uint32_t)s.v.z; w32[3] = (uint32_t)s.v.w;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; e++)
-                                if (keep & (1u << e)) smem_stage[pos++] = (int16_t)s.get(e);
+                                if (kp & (1u << e)) smem_stage[pos++] = (int16_t)s.get(e);
                         }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; e++)
-                            if (keep & (1u << e)) stage[pos++] = (int16_t)s.get(e);
+                            if (kp & (1u << e)) stage[pos++] = (int16_t)s.get(e);
                     }
                 }
                 total += all;
-                if (NT > 32) __syncthreads();
             }
         }
         const int n = total;
