@@ -29,6 +29,7 @@
 //             state machine).
 #pragma once
 #include "sqk_common.cuh"
+#include "sqk_stats_plan.cuh"
 
 #define SQK_STATS_THREADS 128       // CTA size; a read is owned by NT = 32 or 128 of them
 #define SQK_TREE_DEPTH 24
@@ -110,22 +111,13 @@ __device__ double stats_pairwise_heap(Term term, int n, StatsShared &sh)
 {
     const int tid = threadIdx.x % NT;
     constexpr int TEAMS = NT / 8;
-    int depth = 0;
-    for (int len = n; len > 128; depth++) { int half = len / 2; half -= half % 8; len -= half; }
+    const int depth = sqk_tree_depth(n);
     const int slots = 1 << depth;                      // <= SQK_TREE_SLOTS
     const int team = tid >> 3, k = tid & 7;
     for (int j0 = 0; j0 < slots; j0 += TEAMS) {
         const int j = j0 + team;
-        int off = 0, len = n, d = 0;
-        bool mine = j < slots;
-        // walk down: bit (depth-1-d) of j picks the child at level d
-        while (len > 128) {
-            int half = len / 2; half -= half % 8;
-            if ((j >> (depth - 1 - d)) & 1) { off += half; len -= half; } else len = half;
-            d++;
-        }
-        // an early leaf (d < depth) belongs to the slot whose remaining bits are all zero
-        if (mine && d < depth && (j & ((1 << (depth - d)) - 1)) != 0) mine = false;
+        int off = 0, len = 0;
+        const bool mine = sqk_tree_leaf(n, depth, j < slots ? j : 0, &off, &len) && j < slots;
         // every team runs the shuffles; teams without a leaf sum a dummy one at offset 0
         const double v = stats_leaf_sum(term, mine ? off : 0, mine ? len : (n >= 8 ? 8 : n), k);
         if (j < slots && k == 0) sh.leaf[j] = mine ? v : 0.0;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../squigglekit_b200/csrc/sqk_dtw_plan.cuh"
+#include "../squigglekit_b200/csrc/sqk_stats_plan.cuh"
 
 namespace {
 
@@ -161,6 +162,32 @@ int plan_exact(const double *x, int N, const double *y, int n, int32_t *out, dou
     const Hit h = exact_window(x, N, y, 0, n, 0, false);
     out[0] = h.start; out[1] = h.end; *dist = h.dist;
     return 0;
+}
+
+// np.sum(a) the way the stats kernel takes it: leaf sums per slot (sqk_tree_leaf), then a pairwise fold of the slots.
+// Valid for n <= 8192 (the kernel walks the levels above such subtrees separately).
+double stats_tree_sum(const double *a, int n)
+{
+    const int depth = sqk_tree_depth(n), slots = 1 << depth;
+    std::vector<double> v(slots, 0.0);
+    for (int j = 0; j < slots; j++) {
+        int off, len;
+        if (!sqk_tree_leaf(n, depth, j, &off, &len)) continue;
+        const double *p = a + off;
+        double s;
+        if (len < 8) { s = 0.0; for (int i = 0; i < len; i++) s += p[i]; }
+        else {
+            double r[8];
+            for (int k = 0; k < 8; k++) r[k] = p[k];
+            int i = 8;
+            for (; i < len - (len % 8); i += 8) for (int k = 0; k < 8; k++) r[k] += p[i + k];
+            s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            for (; i < len; i++) s += p[i];
+        }
+        v[j] = s;
+    }
+    for (int w = slots; w > 1; w /= 2) for (int i = 0; i < w / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
+    return v[0];
 }
 
 }  // extern "C"

@@ -29,6 +29,8 @@ def harness(tmp_path_factory):
     lib.plan_two_pass.argtypes = [dp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, ip, dp, C.POINTER(C.c_int64)]
     lib.plan_exact.argtypes = [dp, C.c_int, dp, C.c_int, ip, dp]
+    lib.stats_tree_sum.argtypes = [dp, C.c_int]
+    lib.stats_tree_sum.restype = C.c_double
     return lib
 
 
@@ -129,3 +131,16 @@ def test_constant_read_overflows_or_proves(harness):
     got, diag, y = _run(harness, motif, sig, scale="zscale")
     d, _, (px, py) = oracle.dtw_subsequence(motif, y, want_cost=False)
     assert got == (int(py[0]), int(py[-1]), d)
+
+
+def test_stats_tree_order_is_numpys(harness):
+    """The stats kernel sums fl((x-mean)^2) per leaf slot and folds the slots pairwise (sqk_stats_plan.cuh): for every
+    n <= 8192 that must be np.sum's own association, bit for bit (np.std / sklearn's scale depend on it)."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(8192) ** 2 * 1e3 + rng.random(8192)
+    for n in range(1, 8193):
+        if n > 300 and n % 7 and n not in (2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192):
+            continue
+        a = np.ascontiguousarray(base[:n])
+        got = harness.stats_tree_sum(a.ctypes.data_as(C.POINTER(C.c_double)), n)
+        assert got == float(np.sum(a)), n
