@@ -18,7 +18,7 @@ WORKER = textwrap.dedent("""
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.environ["SQK_ROOT"])
-    from squigglekit_b200.dist import allgather_records, env_rank_world, shard_bounds
+    from squigglekit_b200.dist import GatherPipeline, allgather_records, env_rank_world, shard_bounds
 
     rank, world, _ = env_rank_world()
     dist.init_process_group("gloo")
@@ -32,6 +32,20 @@ WORKER = textwrap.dedent("""
     even = torch.full((4, 1, 16), rank, dtype=torch.uint8)
     got = allgather_records(even)
     assert got.shape[0] == 4 * world and all(int(got[4 * r, 0, 0]) == r for r in range(world))
+    # double-buffered per-step gather (bench.py): results of step i stay intact while step i+1 is written
+    pipe = GatherPipeline((3, 1, 16), torch.uint8, torch.device("cpu"), depth=2)
+    outs = []
+    for step in range(5):
+        buf = pipe.local_buffer()
+        buf.fill_(10 * step + rank)
+        outs.append((step, pipe.submit()))
+        if len(outs) == 2:            # the older of the two in-flight results is still valid here
+            st, o = outs.pop(0)
+            pipe.work[st % 2].wait()
+            assert o.shape[0] == 3 * world and all(int(o[3 * r, 0, 0]) == 10 * st + r for r in range(world)), st
+    pipe.drain()
+    st, o = outs.pop(0)
+    assert all(int(o[3 * r, 0, 0]) == 10 * st + r for r in range(world))
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
