@@ -155,7 +155,7 @@ struct sqk_ctx {
     int dtw_plan = SQK_PLAN_AUTO;
     int lb_want_k = 12;   // measured on B200: K=10/L=8 5.85 ms vs K=20/L=4 6.11 ms per 100k x 4096 x 80
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
-    int stats_smem_set32 = -1, stats_smem_set128 = -1;
+    int stats_smem_set32 = -1, stats_smem_set128 = -1, stats_smem_set256 = -1;
 };
 
 struct Guard {   // make the ctx device current for the duration of a call
@@ -309,7 +309,8 @@ static inline int clamp_lim(int v) { return v < -40000 ? -40000 : (v > 40000 ? 4
 template <int NT>
 static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, int *smem_set)
 {
-    constexpr int GROUPS = SQK_STATS_THREADS / NT;
+    constexpr int TPB = StatsCta<NT>::threads;
+    constexpr int GROUPS = TPB / NT;
     const size_t fixed = (sizeof(StatsShared) + 15) & ~(size_t)15;
     // staging capacity per group: the longest read if it fits (2 bytes/sample)
     const int64_t budget = ((int64_t)c->smem_optin - 1024) / GROUPS - (int64_t)fixed;
@@ -324,7 +325,7 @@ static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, c
         *smem_set = dyn;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel<NT>, SQK_STATS_THREADS, dyn));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel<NT>, TPB, dyn));
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (v.n_reads + GROUPS - 1) / GROUPS;
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->n_sms * per_sm));
@@ -336,7 +337,7 @@ static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, c
     }
     cudaEvent_t eb;
     TRY(tick(c, SQK_K_STATS, st, &eb));
-    sqk_stats_kernel<NT><<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
+    sqk_stats_kernel<NT><<<(unsigned)grid, TPB, dyn, st>>>(a);
     CU(cudaGetLastError());
     TRY(tock(eb, st));
     return SQK_OK;
@@ -359,8 +360,13 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     static int force_nt = -1;
     if (force_nt < 0) { const char *e = getenv("SQK_STATS_NT"); force_nt = e ? atoi(e) : 0; }
     const bool warp_per_read = force_nt == 32 && v.max_len <= SQK_HEAP_MAX_N;
-    return warp_per_read ? launch_stats_nt<32>(c, s, st, a, v, &c->stats_smem_set32)
-                         : launch_stats_nt<128>(c, s, st, a, v, &c->stats_smem_set128);
+    if (warp_per_read) return launch_stats_nt<32>(c, s, st, a, v, &c->stats_smem_set32);
+    // Reads so long that their shared-memory staging (2 bytes/sample) leaves room for fewer than four 128-thread CTAs
+    // per SM get 256 threads each: the same staged reads per SM, twice the warps working on them.
+    const int64_t stage_bytes = 2 * std::min<int64_t>(v.max_len, ((int64_t)c->smem_optin - 4096) / 2) + 4096;
+    const bool wide = force_nt == 256 || (force_nt == 0 && 4 * stage_bytes > (int64_t)c->smem_optin);
+    return wide ? launch_stats_nt<256>(c, s, st, a, v, &c->stats_smem_set256)
+                : launch_stats_nt<128>(c, s, st, a, v, &c->stats_smem_set128);
 }
 
 static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_out, sqk_dtw_launcher *fn)

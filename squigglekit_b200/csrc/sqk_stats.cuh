@@ -31,7 +31,9 @@
 #include "sqk_common.cuh"
 #include "sqk_stats_plan.cuh"
 
-#define SQK_STATS_THREADS 128       // CTA size; a read is owned by NT = 32 or 128 of them
+#define SQK_STATS_THREADS 128       // CTA size for NT <= 128; a read is owned by NT = 32, 128 or 256 threads
+#define SQK_STATS_MAX_WARPS 8       // warps per read at most (NT = 256: reads so long that shared memory, not registers,
+                                    // limits the CTAs per SM -- twice the warps per staged read)
 #define SQK_TREE_DEPTH 24
 #define SQK_HIST_BINS 2048          // direct histogram when the outlier window spans <= 2048 raw values
 #define SQK_RADIX_BINS 512          // fallback two-pass radix select (9 + 8 bits)
@@ -63,10 +65,10 @@ struct StatsShared {
         double leaf[SQK_TREE_SLOTS];                  // leaf sums of the pairwise tree (n <= SQK_HEAP_MAX_N), in slot order
     };
     double tree_out;
-    unsigned long long sum_part[4];
-    int warp_tot[4];
-    int scan_tot[2][4][4];                            // compaction pass: [iteration parity][block of the thread][warp]
-    uint32_t scan_part[4];
+    unsigned long long sum_part[SQK_STATS_MAX_WARPS];
+    int warp_tot[SQK_STATS_MAX_WARPS];
+    int scan_tot[2][4][SQK_STATS_MAX_WARPS];          // compaction pass: [iteration parity][block of the thread][warp]
+    uint32_t scan_part[SQK_STATS_MAX_WARPS];
     uint32_t sel[2];
 };
 
@@ -318,10 +320,12 @@ __device__ __forceinline__ int stats_last_below(double limit, double off, double
     return lo;
 }
 
+template <int NT> struct StatsCta { static constexpr int threads = NT > SQK_STATS_THREADS ? NT : SQK_STATS_THREADS; };
+
 template <int NT>
-__global__ void __launch_bounds__(SQK_STATS_THREADS, 6) sqk_stats_kernel(const StatsArgs a)
+__global__ void __launch_bounds__(StatsCta<NT>::threads, NT > SQK_STATS_THREADS ? 2 : 6) sqk_stats_kernel(const StatsArgs a)
 {
-    constexpr int GROUPS = SQK_STATS_THREADS / NT;
+    constexpr int GROUPS = StatsCta<NT>::threads / NT;
     constexpr int WARPS = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x % NT, gi = threadIdx.x / NT, lane = tid & 31, warp = tid >> 5;
