@@ -33,17 +33,17 @@ def main():
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:72s} {vals[i]:>18s} {units[i]}")
-        print("  -- warp stall reasons (pct of warp-active cycles per issue, > 1 %)")
+        print("  -- warp stall reasons (warps stalled per issued instruction, > 0.05)")
         st = []
         for i, h in enumerate(hdr):
-            if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
                 try:
-                    st.append((float(vals[i]), h))
+                    st.append((float(vals[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
                 except ValueError:
                     pass
         for v, h in sorted(st, reverse=True):
-            if v > 1.0:
-                print(f"  {h:92s} {v:8.2f}")
+            if v > 0.05:
+                print(f"   {h:28s} {v:8.3f}")
 
 
 if __name__ == "__main__":
