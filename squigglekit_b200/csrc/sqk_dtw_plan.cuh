@@ -185,7 +185,12 @@ SQK_HD float sqk_lb_thr_u(float thr, float offmax)
 
 #define SQK_LB_THR_INIT 1e30f                     // threshold before the first column (finite: inf <= thr must be false)
 
-SQK_HD int sqk_lb_window(int N) { return 2 * N + 32; }   // columns in front of a cluster's first candidate
+// Columns in front of a cluster's first candidate.  Alignments of an N-point motif span <= 1.43 N columns on the
+// synthetic benchmark reads and <= 1.40 N on the 60 reads of the reference's example_fast5s.tar (163-point example
+// model).  A window that turns out too short taints the minimum and the read is re-run in full -- and a full-length
+// re-run costs the latency of one whole read (~0.6 ms at 4096 samples) however few reads need it: W = 1.5 N + 32 was
+// measured 0.6 ms per 100 k reads SLOWER than 2 N + 32 because 2 of the 100 k reads fell back.  So W is generous.
+SQK_HD int sqk_lb_window(int N) { return 2 * N + 32; }
 
 // Where does the window of a cluster starting at column `lo` begin?  ck[(k) % SQK_LB_CKPT] = number of kept
 // samples in front of refill k (refills fetch `ch` raw samples each, the first at cursor0); n_ref refills have
