@@ -1,14 +1,16 @@
 // sqk_dtw_lb.cuh -- pass 1 of the exact two-pass plan (sqk_dtw_plan.cuh): a float32, cost-only, rounded-down
 // lower bound of the last row of mlpy's subsequence-DTW cost matrix (MotifSeq.py:437), fused with the same
-// int16 -> outlier filter -> normalise front end as the exact kernel.  4 instructions per cell
-// (FADD.RZ, FADD.RM, FMNMX3, FADD.RM) instead of ~12; no start pointers, no float64 in the recurrence.
+// int16 -> outlier filter -> normalise front end as the exact kernel.  3 instructions per cell
+// (FADD.RZ, FMNMX3, FADD.RM) instead of ~12; no start pointers, no float64 in the recurrence (the derivation of
+// the bound -- the U recurrence with the free-start row fed j*w -- is in sqk_dtw_plan.cuh).
 //
-// Same mapping as sqk_dtw_kernel: L lanes per read, K motif rows per lane in registers, skewed wavefront,
-// one __shfl_up per step, normalised samples staged in a per-group shared-memory ring.  The lane that owns the
-// last motif row watches L[j] against the candidate threshold (vote-gated, candidates are rare) and keeps the
-// candidate clusters; refill checkpoints (kept-sample count in front of every refill) let it translate a
-// cluster into the raw position its exact window starts at.  At the end of a read it appends one DtwJob per
-// cluster to the job list consumed by sqk_dtw_kernel<JOBS>.
+// Same mapping as sqk_dtw_kernel: L lanes per read, K motif rows per lane in registers, skewed wavefront (two
+// signal columns per step: two dependency chains per lane), one __shfl_up per column, normalised samples staged
+// in a per-group shared-memory ring.  The lane that owns the last motif row watches U against a per-block
+// threshold (one compare and a branch per two columns; candidates are rare) and keeps the candidate clusters;
+// refill checkpoints (kept-sample count in front of every refill) let it translate a cluster into the raw
+// position its exact window starts at.  At the end of a read it appends one DtwJob per cluster to the job list
+// consumed by sqk_dtw_kernel<JOBS>.
 #pragma once
 #include "sqk_common.cuh"
 #include "sqk_dtw_plan.cuh"
