@@ -144,3 +144,38 @@ def test_stats_tree_order_is_numpys(harness):
         a = np.ascontiguousarray(base[:n])
         got = harness.stats_tree_sum(a.ctypes.data_as(C.POINTER(C.c_double)), n)
         assert got == float(np.sum(a)), n
+
+
+def test_adversarial_shapes_never_violate_the_bound(harness):
+    """Motifs of 7..1024 points in z-score, scaled and raw units, reads of up to 30 k samples with dwell structure,
+    integer plateaus (exact ties) or three-level noise, every lane layout: the lower bound never exceeds mlpy's last
+    row, the cheap per-step test never misses a candidate, and (inside the harness) every result the plan calls
+    proven equals the full float64 recurrence.  Fallbacks are allowed -- they are the plan's answer to such reads."""
+    rng = np.random.default_rng(99)
+    proven = 0
+    for trial in range(100):
+        n = int(rng.choice([7, 16, 33, 80, 163, 400, 1024]))
+        m = int(rng.integers(max(4 * n, 300), 30000 if n < 400 else 12000))
+        kind = trial % 5
+        if kind == 0:
+            motif = rng.standard_normal(n)
+        elif kind == 1:
+            motif = np.repeat(rng.standard_normal(n // 6 + 1), 6)[:n]
+        elif kind == 2:
+            motif = np.repeat(rng.integers(400, 620, n // 8 + 1), 8)[:n].astype(float)      # raw units, scale "none"
+        elif kind == 3:
+            motif = rng.standard_normal(n) * 5
+        else:
+            motif = np.zeros(n)
+        if kind == 2:
+            sig, scale = np.repeat(rng.integers(380, 640, m // 5 + 1), 5)[:m].astype(np.int16), "none"
+        else:
+            sig, _, _ = synth.motifseq_reads_np(1, m, motif if n < 200 and kind < 2 else None, seed=trial)
+            scale = ["zscale", "medmad"][trial % 2]
+            if kind == 4:
+                sig = (np.full(m, 500) + rng.integers(-1, 2, m)).astype(np.int16)
+        got, diag, y = _run(harness, np.ascontiguousarray(motif, dtype=np.float64), sig, scale=scale,
+                            lanes=int(rng.choice([4, 8, 16, 32])), align_off=int(rng.integers(0, 8)))
+        assert diag[4] == 0, (trial, n, m, kind)
+        proven += int(diag[2] == 0)
+    assert proven >= 50
