@@ -37,13 +37,15 @@ def test_struct_layouts_match_header():
     from squigglekit_b200 import _cabi
     assert C.sizeof(_cabi.MotifParams) == 16
     assert C.sizeof(_cabi.SegParams) == 48
+    assert C.sizeof(_cabi.AdapterParams) == 48 and _cabi.AdapterParams.std_scale.offset == 32
     assert _cabi.HIT_DTYPE.itemsize == 16 and _cabi.HIT_DTYPE.fields["dist"][1] == 8
     assert C.sizeof(_cabi.Timing) == 8 * _cabi.K_COUNT + 8 * _cabi.K_COUNT and _cabi.K_COUNT == 5   # enum sqk_kernel_id
 
 
 def test_header_compiles_as_plain_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "sqk.h"\nint main(void){ sqk_hit h; sqk_seg_params p; (void)h; (void)p; return sizeof(sqk_hit) == 16 ? 0 : 1; }\n')
+    src.write_text('#include "sqk.h"\nint main(void){ sqk_hit h; sqk_seg_params p; sqk_adapter_params a = SQK_ADAPTER_DEFAULTS; (void)h; (void)p;\n'
+                   '  return sizeof(sqk_hit) == 16 && sizeof(sqk_adapter_params) == 48 && a.t_end == 5000 && a.lim_hi == 1200 && SQK_K_COUNT == 5 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
