@@ -21,7 +21,8 @@
  *                           enqueues work on the ctx stream (sqk_ctx_set_stream / sqk_ctx_sync).
  *   - return value: 0 = ok, <0 = sqk_status; message via sqk_last_error() (thread-local).
  *   - a ctx is bound to one device and is not thread-safe; use one ctx per host thread.  Device-mode calls
- *     share the ctx's scratch memory in stream order: keep them on ONE stream (or sqk_ctx_sync between streams).
+ *     share the ctx's scratch memory in stream order; the library orders calls that arrive on different streams
+ *     (and host-mode calls behind device-mode ones) with events.
  *   - the caller owns every buffer passed in; the library keeps no reference after return
  *     (device mode: after the stream work has completed).
  *   - there is NO CPU fallback: without a CUDA device sqk_ctx_create fails.
@@ -68,9 +69,12 @@ SQK_API const char *sqk_last_error(void);
 
 SQK_API int sqk_ctx_create(int device, sqk_ctx **out);
 SQK_API int sqk_ctx_destroy(sqk_ctx *ctx);
-/* Run device-mode calls on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
- * stream); NULL restores the ctx's own stream. */
+/* Run device-mode calls on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream).  NULL is a
+ * stream like any other: the legacy default stream (what torch's default stream is).  sqk_ctx_reset_stream goes
+ * back to the ctx's own stream.  Calls arriving on a different stream than the previous device-mode call are
+ * ordered behind it with an event, so the shared ctx scratch is never raced. */
 SQK_API int sqk_ctx_set_stream(sqk_ctx *ctx, void *cuda_stream);
+SQK_API int sqk_ctx_reset_stream(sqk_ctx *ctx);
 SQK_API int sqk_ctx_sync(sqk_ctx *ctx);
 SQK_API int sqk_device_count(int *count);
 /* multiProcessorCount etc. of the ctx device: props[0]=SMs, [1]=max smem/block (bytes),
@@ -232,6 +236,44 @@ SQK_API int sqk_ctx_set_dtw_plan(sqk_ctx *ctx, int plan);
 /* Diagnostics of the most recent two-pass launch of slot 0 (device-mode calls; the last chunk in host mode), first
  * model: out[0] = exact windows run, out[1] = reads re-run over their full length.  Synchronises. */
 SQK_API int sqk_ctx_get_plan_counters(sqk_ctx *ctx, int64_t out[2]);
+
+/* Kernels launched by this ctx since the last reset (every launch is counted where it is made). */
+SQK_API int sqk_ctx_get_launches(sqk_ctx *ctx, int64_t *out, int reset);
+
+/* Which statistics kernel (K1) runs: 0 = automatic (second generation -- bulk-copy staging, no compaction pass -- for
+ * reads of up to 8176 samples, the first generation beyond that and for the reads the second hands back), 1 = first
+ * generation only.  Results are identical bit for bit; the knob exists for A/B measurements and tests. */
+SQK_API int sqk_ctx_set_stats_generation(sqk_ctx *ctx, int generation);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, reads sharded over the ranks.  The only exchange on the path is the
+ * gather of the 16-byte hit records.  Instead of a collective after the kernels, the kernels that PRODUCE a record store
+ * it into the gathered buffer of every peer GPU through P2P-mapped pointers (NVLink): a fused compute + all-gather.
+ *
+ *   every rank:   sqk_device_alloc(gathered buffer [world * n_local * n_models] sqk_hit, flag array)
+ *                 sqk_ipc_export -> exchange the 64-byte handles by any means (torch.distributed, MPI, a file)
+ *                 sqk_ipc_open on every peer's handles
+ *                 sqk_ctx_set_hit_peers(peers' buffer bases, n, first_record = rank * n_local)
+ *                 sqk_ctx_set_flag_peers(all ranks' flag arrays incl. the own one, world, rank)
+ *   per step:     sqk_motifseq(..., SQK_MEM_DEVICE, hits = own block of the own gathered buffer, ...)
+ *                 sqk_peer_signal(step)       -- after the step's kernels, stream-ordered
+ *   to read:      sqk_peer_wait(step)         -- stream-ordered: returns (on the stream) once every rank signalled `step`
+ *
+ * Only device-mode sqk_motifseq publishes.  A buffer may be rewritten by a later step as soon as that step runs: the
+ * caller rotates buffers (sqk_ctx_set_hit_peers per step) and reads a buffer before the ranks reuse it.
+ * ------------------------------------------------------------------------------------- */
+SQK_API int sqk_device_alloc(sqk_ctx *ctx, uint64_t bytes, void **dev_ptr);     /* zero-filled; IPC-exportable */
+SQK_API int sqk_device_free(sqk_ctx *ctx, void *dev_ptr);
+SQK_API int sqk_ipc_export(sqk_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+SQK_API int sqk_ipc_open(sqk_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+SQK_API int sqk_ipc_close(sqk_ctx *ctx, void *dev_ptr);
+/* peers[n_peers]: bases of the OTHER ranks' gathered buffers (device pointers valid on this GPU); record r of this rank
+ * is stored at peers[p][(first_record + r) * n_models + m].  n_peers = 0 turns publication off. */
+SQK_API int sqk_ctx_set_hit_peers(sqk_ctx *ctx, void *const *peers, int n_peers, int64_t first_record);
+/* flag_arrays[n_ranks]: every rank's flag array (uint64[16], zero-filled), the own one at index my_rank. */
+SQK_API int sqk_ctx_set_flag_peers(sqk_ctx *ctx, void *const *flag_arrays, int n_ranks, int my_rank);
+SQK_API int sqk_peer_signal(sqk_ctx *ctx, uint64_t value);
+SQK_API int sqk_peer_wait(sqk_ctx *ctx, uint64_t value);
 
 #ifdef __cplusplus
 }

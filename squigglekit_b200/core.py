@@ -138,6 +138,54 @@ class Context:
         _cabi.check(self._lib.sqk_ctx_get_plan_counters(self._h, out))
         return {"windows": int(out[0]), "fallback_reads": int(out[1])}
 
+    def launches(self, reset: bool = True) -> int:
+        """Kernels this context launched since the last reset (counted by the library at every launch site)."""
+        out = C.c_int64(0)
+        _cabi.check(self._lib.sqk_ctx_get_launches(self._h, C.byref(out), int(reset)))
+        return int(out.value)
+
+    def set_stats_generation(self, gen: int = 0):
+        """0 = automatic, 1 = first-generation statistics kernel only (A/B measurements, tests); same results."""
+        _cabi.check(self._lib.sqk_ctx_set_stats_generation(self._h, int(gen)))
+
+    # ---- multi-GPU publication of hit records (see include/sqk.h; squigglekit_b200.dist.PeerGather drives these) ------
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _cabi.check(self._lib.sqk_device_alloc(self._h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        _cabi.check(self._lib.sqk_device_free(self._h, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        _cabi.check(self._lib.sqk_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        _cabi.check(self._lib.sqk_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        _cabi.check(self._lib.sqk_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def set_hit_peers(self, peers, first_record: int = 0):
+        arr = (C.c_void_p * max(1, len(peers)))(*[C.c_void_p(p) for p in peers])
+        _cabi.check(self._lib.sqk_ctx_set_hit_peers(self._h, arr, len(peers), int(first_record)))
+
+    def set_flag_peers(self, flag_arrays, my_rank: int):
+        arr = (C.c_void_p * max(1, len(flag_arrays)))(*[C.c_void_p(p) for p in flag_arrays])
+        _cabi.check(self._lib.sqk_ctx_set_flag_peers(self._h, arr, len(flag_arrays), int(my_rank)))
+
+    def peer_signal(self, value: int):
+        self._use_torch_stream()
+        _cabi.check(self._lib.sqk_peer_signal(self._h, int(value)))
+
+    def peer_wait(self, value: int):
+        self._use_torch_stream()
+        _cabi.check(self._lib.sqk_peer_wait(self._h, int(value)))
+
     def set_chunk_samples(self, samples: int):
         """Host mode: samples per in-flight chunk of the copy/compute pipeline (0 = default)."""
         _cabi.check(self._lib.sqk_ctx_set_chunk_samples(self._h, int(samples)))

@@ -18,6 +18,7 @@
 #include "sqk_adapter.cuh"
 #include "sqk_f64.cuh"
 #include "sqk_stats.cuh"
+#include "sqk_stats2.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -99,6 +100,7 @@ struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
+    DevBuf redo, mask;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -156,6 +158,19 @@ struct sqk_ctx {
     int lb_want_k = 12;   // measured on B200: K=10/L=8 5.85 ms vs K=20/L=4 6.11 ms per 100k x 4096 x 80
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1, stats_smem_set256 = -1;
+    int stats2_smem_set[5] = {-1, -1, -1, -1, -1};
+    int stats_gen = 0;                // 0 = automatic, 1 = first-generation kernel only (experiments / tests)
+    // device-mode calls share the ctx scratch in stream order: the end of every enqueue is marked with an event and a
+    // call that arrives on a different stream waits for it first
+    PeerOut peers{};                  // multi-GPU publication targets of device-mode sqk_motifseq (sqk_ctx_set_hit_peers)
+    int64_t peer_base = 0;            // first record of this rank in a gathered buffer
+    PeerFlags flags{};
+    int64_t n_launches = 0;           // kernels launched (sqk_ctx_get_launches)
+    cudaEvent_t dev_done = nullptr;
+    cudaStream_t dev_last = nullptr;
+    bool dev_any = false;
+    std::vector<double> model_host;   // what c->model holds on the device (uploads are skipped when nothing changed)
+    HostBuf model_stage;              // pinned staging of the model upload (no implicit sync on the caller's stream)
 };
 
 struct Guard {   // make the ctx device current for the duration of a call
@@ -168,6 +183,65 @@ struct Guard {   // make the ctx device current for the duration of a call
     }
     ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// Host-mode pipelines: when a call fails part-way, earlier chunks may still be copying into the caller's result arrays
+// and their pinned->pageable hand-overs are still queued.  The caller is about to see an error (and may free those
+// arrays): wait for what is in flight and DROP the queued hand-overs instead of leaving them for the next call.
+struct PipeGuard {
+    sqk_ctx *c;
+    bool armed = true;
+    explicit PipeGuard(sqk_ctx *ctx) : c(ctx) {}
+    ~PipeGuard()
+    {
+        if (!armed) return;
+        for (int i = 0; i < 2; i++) {
+            cudaStreamSynchronize(c->slot[i].stream);
+            c->slot[i].n_pend = 0;
+        }
+        cudaGetLastError();
+    }
+};
+
+// Device-mode calls use ctx-level scratch (slot 0, the model buffer): order a call on stream `st` behind the previous
+// device-mode call if that one ran on another stream, and behind host-mode work on the slot streams.
+static int dev_begin(sqk_ctx *c, cudaStream_t st)
+{
+    if (c->dev_any && c->dev_last != st) CU(cudaStreamWaitEvent(st, c->dev_done, 0));
+    return SQK_OK;
+}
+
+static int host_begin(sqk_ctx *c)   // host-mode pipelines run on the slot streams: wait for enqueued device-mode work
+{
+    if (c->dev_any) CU(cudaEventSynchronize(c->dev_done));
+    return SQK_OK;
+}
+
+static int dev_end(sqk_ctx *c, cudaStream_t st)
+{
+    if (!c->dev_done) CU(cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->dev_done, st));
+    c->dev_last = st; c->dev_any = true;
+    return SQK_OK;
+}
+
+// Models are a few hundred bytes: staged through pinned memory, and only when they differ from what the device holds.
+static int upload_models(sqk_ctx *c, const double *models, size_t n_points, cudaStream_t st)
+{
+    const size_t bytes = n_points * sizeof(double);
+    if (c->model.p && c->model_host.size() == n_points && memcmp(c->model_host.data(), models, bytes) == 0) return SQK_OK;
+    // the previous upload (and every kernel reading the old model) must be done before the staging buffer is rewritten
+    if (c->dev_any) CU(cudaEventSynchronize(c->dev_done));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    CU(cudaStreamSynchronize(c->slot[1].stream));
+    TRY(ensure(c->model, bytes));
+    TRY(ensure_host(c->model_stage, bytes));
+    memcpy(c->model_stage.p, models, bytes);
+    c->model_host.clear();
+    CU(cudaMemcpyAsync(c->model.p, c->model_stage.p, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    c->model_host.assign(models, models + n_points);
+    return SQK_OK;
+}
 
 static int tick(sqk_ctx *c, int kid, cudaStream_t st, cudaEvent_t *b_out)
 {
@@ -307,7 +381,8 @@ struct View {                 // a set of reads resident on the device
 static inline int clamp_lim(int v) { return v < -40000 ? -40000 : (v > 40000 ? 40000 : v); }   // samples are int16
 
 template <int NT>
-static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, int *smem_set)
+static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, int *smem_set,
+                           bool timed = true, int64_t max_grid = 0)
 {
     constexpr int TPB = StatsCta<NT>::threads;
     constexpr int GROUPS = TPB / NT;
@@ -328,24 +403,92 @@ static int launch_stats_nt(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, c
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_stats_kernel<NT>, TPB, dyn));
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (v.n_reads + GROUPS - 1) / GROUPS;
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->n_sms * per_sm));
+    int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->n_sms * per_sm));
+    if (max_grid > 0) grid = std::min(grid, max_grid);
     a.cap = (int)cap; a.gstage = nullptr; a.gstage_stride = 0;
     if (v.max_len > cap && a.mode != SQK_STATS_NONE) {
         const int64_t stride = (v.max_len + 7) & ~7ll;
         TRY(ensure(s.gstage, (size_t)grid * GROUPS * stride * sizeof(int16_t)));
         a.gstage = (int16_t *)s.gstage.p; a.gstage_stride = stride;
     }
-    cudaEvent_t eb;
-    TRY(tick(c, SQK_K_STATS, st, &eb));
+    cudaEvent_t eb = nullptr;
+    if (timed) TRY(tick(c, SQK_K_STATS, st, &eb));
     sqk_stats_kernel<NT><<<(unsigned)grid, TPB, dyn, st>>>(a);
     CU(cudaGetLastError());
-    TRY(tock(eb, st));
+    c->n_launches++;
+    if (timed) TRY(tock(eb, st));
     return SQK_OK;
+}
+
+// What the statistics pass left behind for the kernels after it.
+struct StatsOut {
+    bool v2 = false;                  // sqk_stats2_kernel ran; reads on the redo list were done by sqk_stats_kernel
+    const int *redo = nullptr;        // redo list (launch-local read indices) ...
+    const unsigned *n_redo = nullptr; // ... and its length, both in device memory
+    const uint32_t *mask = nullptr;   // segmenter mode: in-range bit masks [n_reads][mask_stride] (not for redo reads)
+    int mask_stride = 0;
+};
+
+// K1, second generation (sqk_stats2.cuh) for reads that fit its shared-memory window; the reads it hands back are
+// worked off by the first-generation kernel through the redo list.
+static int launch_stats2(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, bool want_mask, StatsOut *so)
+{
+    Stats2Args A{};
+    const int cap_units = (int)((std::max<int64_t>(v.max_len, 8) + 14 + 7) / 8);
+    const int nseg = (cap_units + 15) / 16;
+    A.buf_bytes = nseg * 256;
+    A.hist_words = a.mode == SQK_STATS_MEDMAD ? 2 * SQK_S2_MAX_BINS : (a.mode == SQK_STATS_SEGMENTER ? SQK_S2_MAX_BINS : 0);
+    A.mask_words = want_mask ? ((nseg * 4 + 2 + 3) & ~3) : 0;
+    A.mask_stride = 0;
+    if (want_mask) {
+        A.mask_stride = (int)((((v.max_len + 31) / 32) + 3) & ~3ll);
+        if (A.mask_stride < 4) A.mask_stride = 4;
+        TRY(ensure(s.mask, (size_t)v.n_reads * A.mask_stride * sizeof(uint32_t)));
+        A.mask = (uint32_t *)s.mask.p;
+    }
+    TRY(ensure(s.redo, ((size_t)v.n_reads + 4) * sizeof(int)));
+    A.n_redo = (unsigned *)s.redo.p;
+    A.redo = (int *)s.redo.p + 4;
+    CU(cudaMemsetAsync(s.redo.p, 0, 16, st));
+    const int dyn = (int)(((sizeof(S2Shared) + 15) & ~(size_t)15) + 4 * (size_t)(A.hist_words + A.mask_words) + 2 * (size_t)A.buf_bytes);
+    void (*kern)(const Stats2Args) = nullptr;
+    int which = 0;
+    const bool pa = a.mode == SQK_STATS_SEGMENTER && a.pa_offset != nullptr;
+    switch (a.mode) {
+    case SQK_STATS_ZSCALE: kern = sqk_stats2_kernel<SQK_STATS_ZSCALE, false>; which = 0; break;
+    case SQK_STATS_MEDMAD: kern = sqk_stats2_kernel<SQK_STATS_MEDMAD, false>; which = 1; break;
+    case SQK_STATS_NONE: kern = sqk_stats2_kernel<SQK_STATS_NONE, false>; which = 2; break;
+    default:
+        if (pa) { kern = sqk_stats2_kernel<SQK_STATS_SEGMENTER, true>; which = 4; }
+        else { kern = sqk_stats2_kernel<SQK_STATS_SEGMENTER, false>; which = 3; }
+        break;
+    }
+    if (dyn > c->stats2_smem_set[which]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        c->stats2_smem_set[which] = dyn;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SQK_S2_THREADS, dyn));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * per_sm));
+    A.s = a;
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_STATS, st, &eb));
+    kern<<<(unsigned)grid, SQK_S2_THREADS, dyn, st>>>(A);
+    CU(cudaGetLastError());
+    c->n_launches++;
+    // the reads it handed back (more outliers than its exception list holds, windows wider than its histogram)
+    a.list = A.redo; a.n_list = A.n_redo; a.extra_flags = SQK_FLAG_NO_MASK;
+    so->v2 = true; so->redo = A.redo; so->n_redo = A.n_redo; so->mask = A.mask; so->mask_stride = A.mask_stride;
+    const int rc = launch_stats_nt<128>(c, s, st, a, v, &c->stats_smem_set128, /*timed=*/false, /*max_grid=*/c->n_sms);
+    TRY(tock(eb, st));
+    return rc;
 }
 
 static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
                         double std_scale, int32_t *d_nkept, const double *d_pa_off = nullptr,
-                        const double *d_pa_scale = nullptr, int t_start = 0, int t_end = 0)
+                        const double *d_pa_scale = nullptr, int t_start = 0, int t_end = 0, StatsOut *so = nullptr,
+                        bool want_mask = false)
 {
     lo = clamp_lim(lo); hi = clamp_lim(hi);
     TRY(ensure(s.stats, (size_t)v.n_reads * sizeof(ReadStats)));
@@ -356,6 +499,12 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     a.mode = mode; a.lo = lo; a.hi = hi; a.num = num; a.std_scale = std_scale;
     a.pa_offset = d_pa_off; a.pa_scale = d_pa_scale;
     a.t_start = t_start; a.t_end = t_end;
+    static int env_gen = -1;
+    if (env_gen < 0) { const char *e = getenv("SQK_STATS_GEN"); env_gen = e ? atoi(e) : 0; }   // experiments: 1 = first generation only
+    const int gen = c->stats_gen ? c->stats_gen : env_gen;
+    StatsOut local;
+    if (gen != 1 && mode != SQK_STATS_ADAPTER && v.max_len <= SQK_S2_MAX_LEN && v.n_reads < 0x7ffffff0LL)
+        return launch_stats2(c, s, st, a, v, want_mask, so ? so : &local);
     // one CTA per read; the warp-per-read form (SQK_STATS_NT=32, reads <= 8192 samples) is kept for experiments
     static int force_nt = -1;
     if (force_nt < 0) { const char *e = getenv("SQK_STATS_NT"); force_nt = e ? atoi(e) : 0; }
@@ -470,7 +619,7 @@ static int check_motif_params(const sqk_motif_params *p)
 // stats + the DTW of every model over a device-resident View; d_hits is [n_reads][n_models]
 static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
                             const double *h_models, const int32_t *h_model_offsets, int n_models,
-                            const sqk_motif_params *p, sqk_hit *d_hits, int32_t *d_nkept)
+                            const sqk_motif_params *p, sqk_hit *d_hits, int32_t *d_nkept, bool publish = false)
 {
     if (v.n_reads == 0) return SQK_OK;
     if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
@@ -492,12 +641,22 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.lo = clamp_lim(p->lo); a.hi = clamp_lim(p->hi);
         a.hits = d_hits + m; a.hit_stride = n_models;
         a.counter = ctr;
+        PeerOut po{};         // this model's column of this rank's block in every peer's gathered buffer
+        if (publish)
+            for (int q = 0; q < c->peers.n; q++) po.peer[po.n++] = c->peers.peer[q] + c->peer_base * n_models + m;
+        const unsigned pub_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((v.n_reads + 255) / 256, 2 * c->n_sms));
         cudaEvent_t eb;
         int LL = 0, LK = 0;   // shape of the lower-bound kernel
         if (L < 4 || !want_two_pass(c, p, N, v.max_len) || !pick_lb_shape(c, N, &LL, &LK)) {   // motifs of <= 4 points run one thread per read: single pass
             TRY(tick(c, SQK_K_DTW, st, &eb));
             cudaError_t e = fn(K, a, c->n_sms, st);
             if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+            c->n_launches++;
+            if (po.n) {
+                sqk_publish_kernel<<<pub_grid, 256, 0, st>>>(a.hits, a.hit_stride, nullptr, nullptr, (int)v.n_reads, po);
+                CU(cudaGetLastError());
+                c->n_launches++;
+            }
             TRY(tock(eb, st));
             continue;
         }
@@ -538,6 +697,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         f.hits = a.hits; f.hit_stride = a.hit_stride;
         f.base = v.base; f.offsets = v.offsets; f.read0 = v.read0; f.stats = a.stats;
         f.fb_jobs = (DtwJob *)s.fbjobs.p; f.n_fb = ctr + 3;
+        f.po = po;
         sqk_dtw_finalize_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(f);
         CU(cudaGetLastError());
         a.counter = ctr + 4;
@@ -545,6 +705,12 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.job_out = a.hits; a.job_out_stride = a.hit_stride;
         e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        c->n_launches += 4;                      // lower-bound scan, windows, finalize, fallback
+        if (po.n) {                              // the (few) reads the fallback just wrote
+            sqk_publish_kernel<<<8, 256, 0, st>>>(a.hits, a.hit_stride, f.fb_jobs, ctr + 3, (int)v.n_reads, po);
+            CU(cudaGetLastError());
+            c->n_launches++;
+        }
         TRY(tock(eb, st));
     }
     return SQK_OK;
@@ -566,8 +732,9 @@ static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v
     if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
     const double fm = std::ceil((double)p->window * p->stall_len);
     const int first_min = fm > 2e9 ? 2000000000 : (fm < -2e9 ? -2000000000 : (int)fm);
+    StatsOut so;
     TRY(launch_stats(c, s, st, v, SQK_STATS_SEGMENTER, p->lim_lo, p->lim_hi, p->num, p->std_scale, nullptr, d_pa_off,
-                     d_pa_scale));
+                     d_pa_scale, 0, 0, &so, /*want_mask=*/true));
     FsmArgs a{};
     a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
     a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
@@ -579,8 +746,20 @@ static int enqueue_segmenter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v
     const unsigned grid = (unsigned)((v.n_reads + SQK_FSM_THREADS - 1) / SQK_FSM_THREADS);
     cudaEvent_t eb;
     TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
+    if (so.v2 && so.mask) {
+        // the state machine on the bit masks sqk_stats2_kernel emitted; the (few) reads of the redo list sample by sample
+        FsmMaskArgs m{};
+        m.mask = so.mask; m.mask_stride = so.mask_stride; m.n_reads = (int)v.n_reads; m.stats = a.stats;
+        m.error = a.error; m.corrector = a.corrector; m.window = a.window; m.seg_dist = a.seg_dist;
+        m.first_min = a.first_min; m.max_segs = a.max_segs; m.segs = d_segs; m.n_segs = d_nsegs;
+        sqk_fsm_mask_kernel<<<grid, SQK_FSM_THREADS, 0, st>>>(m);
+        CU(cudaGetLastError());
+        c->n_launches++;
+        a.list = so.redo; a.n_list = so.n_redo;
+    }
     sqk_fsm_kernel<<<grid, SQK_FSM_THREADS, 0, st>>>(a);
     CU(cudaGetLastError());
+    c->n_launches++;
     TRY(tock(eb, st));
     return SQK_OK;
 }
@@ -614,6 +793,7 @@ static int enqueue_adapter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, 
     TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
     sqk_adapter_fsm_kernel<<<grid, SQK_ADAPTER_THREADS, 0, st>>>(a);
     CU(cudaGetLastError());
+    c->n_launches++;
     TRY(tock(eb, st));
     return SQK_OK;
 }
@@ -644,6 +824,7 @@ static int launch_f64_front(sqk_ctx *c, Slot &s, cudaStream_t st, const View64 &
     TRY(tick(c, SQK_K_STATS, st, &eb));
     sqk_f64_front_kernel<<<(unsigned)grid, SQK_STATS_THREADS, dyn, st>>>(a);
     CU(cudaGetLastError());
+    c->n_launches++;
     TRY(tock(eb, st));
     return SQK_OK;
 }
@@ -674,6 +855,7 @@ static int enqueue_motifseq_f64(sqk_ctx *c, Slot &s, cudaStream_t st, const View
         a.prenorm = (const double *)s.ynorm.p - v.sample0;
         cudaEvent_t eb;
         TRY(tick(c, SQK_K_DTW, st, &eb));
+        c->n_launches++;
         cudaError_t e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
         TRY(tock(eb, st));
@@ -722,6 +904,7 @@ static int device_max_len(sqk_ctx *c, cudaStream_t st, const int64_t *d_offsets,
     const int grid = (int)std::min<int64_t>(4 * c->n_sms, (n_reads + 255) / 256);
     sqk_max_len_kernel<<<std::max(grid, 1), 256, 0, st>>>(d_offsets, n_reads, (unsigned long long *)c->scratch8.p);
     CU(cudaGetLastError());
+    c->n_launches++;
     unsigned long long h = 0;
     CU(cudaMemcpyAsync(&h, c->scratch8.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -834,11 +1017,13 @@ int sqk_ctx_destroy(sqk_ctx *c)
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
         release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes);
-        release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres);
+        release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres); release(s.redo); release(s.mask);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     release(c->model); release(c->scratch8);
+    if (c->model_stage.p) cudaFreeHost(c->model_stage.p);
+    if (c->dev_done) cudaEventDestroy(c->dev_done);
     delete c;
     return SQK_OK;
 }
@@ -847,7 +1032,15 @@ int sqk_ctx_set_stream(sqk_ctx *c, void *cuda_stream)
 {
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
     c->user_stream = (cudaStream_t)cuda_stream;
-    c->use_user_stream = true;     // NULL is a valid stream (the legacy default stream)
+    c->use_user_stream = true;     // NULL is a valid stream (the legacy default stream, torch's default stream)
+    return SQK_OK;
+}
+
+int sqk_ctx_reset_stream(sqk_ctx *c)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    c->user_stream = nullptr;
+    c->use_user_stream = false;
     return SQK_OK;
 }
 
@@ -940,6 +1133,129 @@ int sqk_ctx_set_dtw_lanes(sqk_ctx *c, int lanes)
     return SQK_OK;
 }
 
+int sqk_ctx_get_launches(sqk_ctx *c, int64_t *out, int reset)
+{
+    if (!c || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    *out = c->n_launches;
+    if (reset) c->n_launches = 0;
+    return SQK_OK;
+}
+
+int sqk_ctx_set_stats_generation(sqk_ctx *c, int gen)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (gen < 0 || gen > 2) return fail(SQK_ERR_ARG, "generation must be 0 (automatic), 1 or 2");
+    c->stats_gen = gen;
+    return SQK_OK;
+}
+
+// ---- multi-GPU publication (one process per GPU) ------------------------------------------------------------------
+int sqk_device_alloc(sqk_ctx *c, uint64_t bytes, void **out)
+{
+    if (!c || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    Guard g(c->device);
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SQK_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    CU(cudaMemset(*out, 0, bytes ? bytes : 1));
+    return SQK_OK;
+}
+
+int sqk_device_free(sqk_ctx *c, void *p)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    Guard g(c->device);
+    if (p) CU(cudaFree(p));
+    return SQK_OK;
+}
+
+int sqk_ipc_export(sqk_ctx *c, void *dev_ptr, unsigned char handle[64])
+{
+    if (!c || !dev_ptr || !handle) return fail(SQK_ERR_ARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    Guard g(c->device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return SQK_OK;
+}
+
+int sqk_ipc_open(sqk_ctx *c, const unsigned char handle[64], void **out)
+{
+    if (!c || !handle || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    Guard g(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SQK_OK;
+}
+
+int sqk_ipc_close(sqk_ctx *c, void *p)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    Guard g(c->device);
+    if (p) CU(cudaIpcCloseMemHandle(p));
+    return SQK_OK;
+}
+
+int sqk_ctx_set_hit_peers(sqk_ctx *c, void *const *peers, int n_peers, int64_t first_record)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_peers < 0 || n_peers > SQK_MAX_PEERS) return fail(SQK_ERR_ARG, "n_peers must be 0..%d", SQK_MAX_PEERS);
+    if (n_peers > 0 && !peers) return fail(SQK_ERR_ARG, "peers is NULL");
+    if (first_record < 0) return fail(SQK_ERR_ARG, "first_record < 0");
+    c->peers = PeerOut{};
+    for (int p = 0; p < n_peers; p++) {
+        if (!peers[p]) return fail(SQK_ERR_ARG, "peers[%d] is NULL", p);
+        c->peers.peer[p] = (sqk_hit *)peers[p];
+    }
+    c->peers.n = n_peers;
+    c->peer_base = first_record;
+    return SQK_OK;
+}
+
+int sqk_ctx_set_flag_peers(sqk_ctx *c, void *const *flag_arrays, int n_ranks, int my_rank)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (n_ranks < 0 || n_ranks > SQK_MAX_PEERS) return fail(SQK_ERR_ARG, "n_ranks must be 0..%d", SQK_MAX_PEERS);
+    if (n_ranks > 0 && (!flag_arrays || my_rank < 0 || my_rank >= n_ranks)) return fail(SQK_ERR_ARG, "bad flag arguments");
+    c->flags = PeerFlags{};
+    for (int p = 0; p < n_ranks; p++) {
+        if (!flag_arrays[p]) return fail(SQK_ERR_ARG, "flag_arrays[%d] is NULL", p);
+        c->flags.arr[p] = (unsigned long long *)flag_arrays[p];
+    }
+    c->flags.n = n_ranks; c->flags.self = my_rank;
+    return SQK_OK;
+}
+
+int sqk_peer_signal(sqk_ctx *c, uint64_t value)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (c->flags.n == 0) return SQK_OK;
+    Guard g(c->device);
+    cudaStream_t st = device_stream(c);
+    TRY(dev_begin(c, st));
+    sqk_peer_signal_kernel<<<1, 32, 0, st>>>(c->flags, (unsigned long long)value);
+    CU(cudaGetLastError());
+    c->n_launches++;
+    TRY(dev_end(c, st));
+    return SQK_OK;
+}
+
+int sqk_peer_wait(sqk_ctx *c, uint64_t value)
+{
+    if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
+    if (c->flags.n == 0) return SQK_OK;
+    Guard g(c->device);
+    cudaStream_t st = device_stream(c);
+    TRY(dev_begin(c, st));
+    sqk_peer_wait_kernel<<<1, 32, 0, st>>>(c->flags, (unsigned long long)value);
+    CU(cudaGetLastError());
+    c->n_launches++;
+    TRY(dev_end(c, st));
+    return SQK_OK;
+}
+
 int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
                  const double *models, const int32_t *model_offsets, int32_t n_models, const sqk_motif_params *p, int mem,
                  sqk_hit *hits, int32_t *n_kept)
@@ -956,20 +1272,22 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     Guard g(c->device);
     if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
 
-    // models are tiny: always staged from the host copy (models / model_offsets are host pointers in both modes)
-    const size_t model_bytes = (size_t)model_offsets[n_models] * sizeof(double);
-    TRY(ensure(c->model, model_bytes));
+    // models are tiny: staged from the host copy when they change (models / model_offsets are host pointers in both modes)
+    const size_t model_points = (size_t)model_offsets[n_models];
 
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
-        CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, st));
+        TRY(upload_models(c, models, model_points, st));
+        TRY(dev_begin(c, st));
         if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
         // device mode: the caller's allocation bounds are unknown, so [offsets[0], offsets[n]) delimits what the
         // kernels may touch (resolve_bounds): 16-byte blocks sticking out of it are read sample by sample.
-        TRY(enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, models, model_offsets, n_models, p, hits, n_kept));
-        return SQK_OK;
+        const int rc = enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, models, model_offsets, n_models, p, hits, n_kept,
+                                        /*publish=*/c->peers.n > 0);
+        TRY(dev_end(c, st));
+        return rc;
     }
 
     // ---- host mode: chunked, double-buffered H2D | stats+DTW | D2H ---------------------------
@@ -981,11 +1299,12 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
         maxlen = std::max(maxlen, d);
     }
     if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
-    CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
-    CU(cudaStreamSynchronize(c->slot[0].stream));
+    TRY(host_begin(c));
+    TRY(upload_models(c, models, model_points, c->slot[0].stream));
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
     const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
         cudaStream_t st = s.stream;
@@ -1006,6 +1325,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     }
     TRY(recycle(c->slot[0]));
     TRY(recycle(c->slot[1]));
+    pg.armed = false;
     return SQK_OK;
 }
 
@@ -1030,11 +1350,14 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        TRY(dev_begin(c, st));
         if (max_read_len <= 0) TRY(device_max_len(c, st, offsets, n_reads, &max_read_len));
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
-        if (ap) TRY(enqueue_adapter(c, c->slot[0], st, v, ap, segs, n_segs));
-        else TRY(enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale));
-        return SQK_OK;
+        int rc;
+        if (ap) rc = enqueue_adapter(c, c->slot[0], st, v, ap, segs, n_segs);
+        else rc = enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale);
+        TRY(dev_end(c, st));
+        return rc;
     }
 
     if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
@@ -1048,6 +1371,8 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
     const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    TRY(host_begin(c));
+    PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
         cudaStream_t st = s.stream;
@@ -1077,6 +1402,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     }
     TRY(recycle(c->slot[0]));
     TRY(recycle(c->slot[1]));
+    pg.armed = false;
     return SQK_OK;
 }
 
@@ -1097,25 +1423,28 @@ int sqk_motifseq_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, 
         if (model_offsets[m + 1] - model_offsets[m] < 1) return fail(SQK_ERR_ARG, "model %d is empty", m);
     Guard g(c->device);
     if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
-    const size_t model_bytes = (size_t)model_offsets[n_models] * sizeof(double);
-    TRY(ensure(c->model, model_bytes));
+    const size_t model_points = (size_t)model_offsets[n_models];
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
-        CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, st));
+        TRY(upload_models(c, models, model_points, st));
+        TRY(dev_begin(c, st));
         int64_t s0 = 0, s1 = 0;
         TRY(device_sample_range(st, offsets, n_reads, &s0, &s1));
         View64 v{signals, offsets, 0, n_reads, s0, s1 - s0};
-        return enqueue_motifseq_f64(c, c->slot[0], st, v, (const double *)c->model.p, model_offsets, n_models, p, hits, n_kept);
+        const int rc = enqueue_motifseq_f64(c, c->slot[0], st, v, (const double *)c->model.p, model_offsets, n_models, p, hits, n_kept);
+        TRY(dev_end(c, st));
+        return rc;
     }
     if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
     for (int64_t r = 0; r < n_reads; r++)
         if (offsets[r + 1] < offsets[r]) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
-    CU(cudaMemcpyAsync(c->model.p, models, model_bytes, cudaMemcpyHostToDevice, c->slot[0].stream));
-    CU(cudaStreamSynchronize(c->slot[0].stream));
+    TRY(host_begin(c));
+    TRY(upload_models(c, models, model_points, c->slot[0].stream));
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
     const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
         cudaStream_t st = s.stream;
@@ -1136,6 +1465,7 @@ int sqk_motifseq_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, 
     }
     TRY(recycle(c->slot[0]));
     TRY(recycle(c->slot[1]));
+    pg.armed = false;
     return SQK_OK;
 }
 
@@ -1154,10 +1484,13 @@ int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets,
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
         if (!signals) return fail(SQK_ERR_ARG, "signals is NULL");
+        TRY(dev_begin(c, st));
         int64_t s0 = 0, s1 = 0;
         TRY(device_sample_range(st, offsets, n_reads, &s0, &s1));
         View64 v{signals, offsets, 0, n_reads, s0, s1 - s0};
-        return enqueue_segmenter_f64(c, c->slot[0], st, v, p, segs, n_segs);
+        const int rc = enqueue_segmenter_f64(c, c->slot[0], st, v, p, segs, n_segs);
+        TRY(dev_end(c, st));
+        return rc;
     }
     if (!signals && offsets[n_reads] > offsets[0]) return fail(SQK_ERR_ARG, "signals is NULL");
     for (int64_t r = 0; r < n_reads; r++)
@@ -1165,6 +1498,8 @@ int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets,
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
     const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    TRY(host_begin(c));
+    PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
         cudaStream_t st = s.stream;
@@ -1185,6 +1520,7 @@ int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets,
     }
     TRY(recycle(c->slot[0]));
     TRY(recycle(c->slot[1]));
+    pg.armed = false;
     return SQK_OK;
 }
 
@@ -1226,10 +1562,11 @@ int sqk_motifseq_trace(sqk_ctx *c, const int16_t *signal, int64_t n_samples, con
     TRY(ensure(s.offsets, 2 * sizeof(int64_t)));
     TRY(ensure(s.hits, sizeof(sqk_hit)));
     TRY(ensure(s.nkept, sizeof(int32_t)));
-    TRY(ensure(c->model, (size_t)n_model * sizeof(double)));
+    TRY(host_begin(c));
+    TRY(upload_models(c, model, (size_t)n_model, st));
     CU(cudaMemcpyAsync(s.signals.p, signal, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->model.p, model, (size_t)n_model * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // offs lives on this stack frame
     View v{(const int16_t *)s.signals.p, 0, n_samples, (const int64_t *)s.offsets.p, 0, 1, n_samples};
     const int32_t mo[2] = {0, n_model};
     TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, model, mo, 1, p, (sqk_hit *)s.hits.p, (int32_t *)s.nkept.p));

@@ -25,6 +25,7 @@ static_assert(sizeof(ReadStats) == 40, "ReadStats layout");
 
 #define SQK_FLAG_DEGENERATE 1
 #define SQK_FLAG_TOO_LONG 2     // read longer than the max_read_len the caller declared: not processed
+#define SQK_FLAG_NO_MASK 4      // segmenter: no in-range bit mask was emitted for this read (sqk_fsm_kernel takes it)
 
 // convert_to_pA_numpy + np.round(.., 2)  (segmenter.py:515-517, 345-349): every op rounds once, as numpy's
 //   (d + offset) * raw_unit ; multiply by 100 ; rint ; divide by 100.

@@ -377,6 +377,23 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 }
 
 // Combine the window results of every read; reads that are not proven get a full-length job in the fallback list.
+// Multi-GPU publication of hit records (one process per GPU): besides the local `hits` array, a record is stored into the
+// gathered buffer of every peer GPU through P2P-mapped pointers (NVLink stores issued by the kernel that produced the
+// record -- a fused compute + all-gather; no collective kernel).  peer[p] points at this rank's block in peer p's buffer,
+// already offset to the model column, so record r goes to peer[p][r * hit_stride].
+#define SQK_MAX_PEERS 16
+struct PeerOut {
+    sqk_hit *peer[SQK_MAX_PEERS];
+    int n;                      // 0 = single GPU: nothing to publish
+};
+
+__device__ __forceinline__ void sqk_publish(const PeerOut &po, int64_t at, const sqk_hit &h)
+{
+    // 16-byte records: one vector store per peer; consecutive threads write consecutive records (coalesced over NVLink)
+    const int4 v = *reinterpret_cast<const int4 *>(&h);
+    for (int p = 0; p < po.n; p++) *reinterpret_cast<int4 *>(po.peer[p] + at) = v;
+}
+
 struct FinalizeArgs {
     const LbRead *reads;
     const sqk_hit *jobres;     // [n_reads][SQK_LB_MAX_CLUSTERS]
@@ -385,6 +402,7 @@ struct FinalizeArgs {
     const int16_t *base; const int64_t *offsets; int64_t read0;
     const ReadStats *stats;
     DtwJob *fb_jobs; unsigned int *n_fb;
+    PeerOut po;
 };
 
 static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
@@ -392,7 +410,10 @@ static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_reads) return;
     const LbRead rec = a.reads[r];
-    if (rec.n_jobs < 0) return;                        // status hit already written by pass 1
+    if (rec.n_jobs < 0) {                              // status hit already written by pass 1: only forward it
+        if (a.po.n) sqk_publish(a.po, (int64_t)r * a.hit_stride, a.hits[(int64_t)r * a.hit_stride]);
+        return;
+    }
     SqkHitLite res[SQK_LB_MAX_CLUSTERS], best;
     const int nj = rec.n_jobs < SQK_LB_MAX_CLUSTERS ? rec.n_jobs : SQK_LB_MAX_CLUSTERS;
     for (int q = 0; q < nj; q++) {
@@ -402,10 +423,49 @@ static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
     if (sqk_lb_decide(rec, res, &best)) {
         sqk_hit h; h.start = best.start; h.end = best.end; h.dist = best.dist;
         a.hits[(int64_t)r * a.hit_stride] = h;
+        sqk_publish(a.po, (int64_t)r * a.hit_stride, h);
     } else {
         DtwJob jb;
         jb.cursor = aligned_block_start(a.base, a.offsets[a.read0 + r]);
         jb.read = r; jb.col0 = 0; jb.n_cols = a.stats[r].n_kept; jb.arg_lo = 0; jb.tainted = 0; jb.out = r;
         a.fb_jobs[atomicAdd(a.n_fb, 1u)] = jb;
+    }
+}
+
+// Publication of records that other kernels wrote into the local array: the reads of a job list (the full-length
+// fallback of the two-pass plan; usually empty) or, with list == nullptr, all reads (single-pass plan).
+static __global__ void sqk_publish_kernel(const sqk_hit *hits, int hit_stride, const DtwJob *list, const unsigned int *n_list,
+                                          int n_reads, PeerOut po)
+{
+    const int n = list ? (int)*n_list : n_reads;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = list ? list[i].read : i;
+        sqk_publish(po, (int64_t)r * hit_stride, hits[(int64_t)r * hit_stride]);
+    }
+}
+
+// One flag per (step, peer): after the kernels of a step, every rank writes the step number into its slot of every
+// peer's flag array; a consumer waits until all slots of its own array have reached the step it wants to read.
+struct PeerFlags {
+    unsigned long long *arr[SQK_MAX_PEERS];   // arr[p] = flag array of peer p (SQK_MAX_PEERS slots)
+    int n, self;
+};
+
+static __global__ void sqk_peer_signal_kernel(PeerFlags f, unsigned long long value)
+{
+    const int p = threadIdx.x;
+    if (p < f.n) {
+        __threadfence_system();               // (the records were stored by earlier kernels of this stream)
+        *reinterpret_cast<volatile unsigned long long *>(f.arr[p] + f.self) = value;
+    }
+}
+
+static __global__ void sqk_peer_wait_kernel(PeerFlags f, unsigned long long value)
+{
+    const int q = threadIdx.x;
+    if (q < f.n) {
+        const volatile unsigned long long *slot = f.arr[f.self] + q;
+        while (*slot < value) __nanosleep(200);
+        __threadfence_system();
     }
 }

@@ -57,6 +57,9 @@ struct StatsArgs {
     int cap;                  // shared-memory staging capacity per group (samples, multiple of 64)
     int16_t *gstage;          // global staging rows for reads longer than cap (or null)
     int64_t gstage_stride;
+    const int *list;          // optional work list (launch-local read indices) instead of all n_reads reads ...
+    const unsigned int *n_list;   // ... and its length (device memory): the redo list of sqk_stats2_kernel
+    int extra_flags;          // OR-ed into ReadStats.flags (SQK_FLAG_NO_MASK for redo reads)
 };
 
 struct StatsShared {
@@ -338,7 +341,9 @@ __global__ void __launch_bounds__(StatsCta<NT>::threads, NT > SQK_STATS_THREADS 
     const bool pa_mode = (a.mode == SQK_STATS_SEGMENTER && a.pa_offset != nullptr);
     const int64_t slot = (int64_t)blockIdx.x * GROUPS + gi;
 
-    for (int64_t i = slot; i < a.n_reads; i += (int64_t)gridDim.x * GROUPS) {
+    const int64_t n_items = a.list ? (int64_t)*a.n_list : a.n_reads;
+    for (int64_t item = slot; item < n_items; item += (int64_t)gridDim.x * GROUPS) {
+        const int64_t i = a.list ? (int64_t)a.list[item] : item;
         const int64_t r = a.read0 + i;
         const int64_t begin = a.offsets[r];
         int64_t len = a.offsets[r + 1] - begin;
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(StatsCta<NT>::threads, NT > SQK_STATS_THREADS 
             // longer than the max_read_len the caller declared: no staging row was provisioned for it
             if (tid == 0) {
                 ReadStats bad;
-                bad.center = 0.0; bad.scale = 1.0; bad.n_kept = 0; bad.flags = SQK_FLAG_TOO_LONG;
+                bad.center = 0.0; bad.scale = 1.0; bad.n_kept = 0; bad.flags = SQK_FLAG_TOO_LONG | a.extra_flags;
                 bad.seg_lo = 0; bad.seg_hi = -1; bad.out_lo = 1; bad.out_hi = 0;
                 a.stats[i] = bad;
                 if (a.n_kept_out) a.n_kept_out[i] = -1;
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(StatsCta<NT>::threads, NT > SQK_STATS_THREADS 
         stats_sync<NT>();   // staged samples visible to the whole group
 
         ReadStats out;
-        out.center = 0.0; out.scale = 1.0; out.n_kept = n; out.flags = 0; out.seg_lo = 0; out.seg_hi = -1;
+        out.center = 0.0; out.scale = 1.0; out.n_kept = n; out.flags = a.extra_flags; out.seg_lo = 0; out.seg_hi = -1;
         out.out_lo = out_lo; out.out_hi = out_hi;
 
         double sd = 0.0;

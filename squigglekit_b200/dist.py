@@ -1,7 +1,12 @@
 """Multi-GPU plumbing: reads are independent, so they shard as contiguous blocks over ranks
-(one process per GPU) and the only exchange is ONE all-gather of the fixed-size hit records at
-the end.  torch.distributed is the transport (NCCL over NVLink on the GPU box,
-gloo in the CPU tests); there is no collective inside the data path.
+(one process per GPU) and the only exchange is the gather of the fixed-size hit records at the end
+of a step.  Two transports:
+
+* :class:`PeerGather` -- the kernels that produce a record store it straight into every peer's
+  gathered buffer through P2P-mapped pointers (NVLink): a fused compute + all-gather with no
+  collective kernel on the SMs.  torch.distributed only carries the 64-byte IPC handles at set-up.
+* :func:`allgather_records` / :class:`GatherPipeline` -- ``all_gather_into_tensor`` (NCCL over NVLink
+  on the GPU box, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -52,10 +57,10 @@ class GatherPipeline:
     step-to-step skew between GPUs is absorbed instead of being paid at every step.  ``drain()`` waits for everything.
     """
 
-    def __init__(self, shape, dtype, device, depth: int = 2):
+    def __init__(self, shape, dtype, device, depth: int = 2, enabled: bool = True):
         import torch
         import torch.distributed as dist
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.world = dist.get_world_size() if (enabled and dist.is_initialized()) else 1
         self.depth = depth
         self.local = [torch.empty(shape, dtype=dtype, device=device) for _ in range(depth)]
         self.out = [torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=device) for _ in range(depth)]
@@ -84,3 +89,97 @@ class GatherPipeline:
             if self.work[k] is not None:
                 self.work[k].wait()
                 self.work[k] = None
+
+    def close(self):
+        self.drain()
+
+
+class _DevView:
+    """Expose a raw device allocation to torch through the CUDA array interface."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Gather of the hit records of a device-mode ``Context.motifseq`` call without a collective: the kernels that
+    produce a record store it into the gathered buffer of every rank (their own through ``out=``, the others through
+    P2P-mapped pointers obtained once over CUDA IPC), and one flag per step and peer says when a rank is done.
+
+    ``local_buffer()`` -> the uint8 tensor [n_local, n_models, 16] the next step must pass as ``out=`` (this rank's block
+    of its own gathered buffer); ``submit()`` signals the step and returns the gathered tensor [world * n_local,
+    n_models, 16] of that step (complete after ``drain()``, or after ``wait(step)``).  ``depth`` buffers rotate: a step
+    overwrites the buffer of the step ``depth`` before it, so read a result before the ranks get that far ahead.
+    """
+
+    def __init__(self, ctx, n_local: int, n_models: int, device, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.depth, self.n_local, self.n_models = ctx, depth, n_local, n_models
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if self.world > 16:
+            raise ValueError("PeerGather supports up to 16 ranks (one node)")
+        self.rec_bytes = 16 * n_models
+        self.slot_bytes = self.world * n_local * self.rec_bytes
+        self.bufs = [ctx.device_alloc(max(self.slot_bytes, 16)) for _ in range(depth)]
+        self.flags = ctx.device_alloc(16 * 8)
+        mine = [ctx.ipc_export(p) for p in self.bufs] + [ctx.ipc_export(self.flags)]
+        everyone = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, mine)
+        else:
+            everyone[0] = mine
+        self.opened = []
+        self.peer_bufs = [[] for _ in range(depth)]       # per buffer: the OTHER ranks' bases, as seen from this GPU
+        flag_ptrs = []
+        for q in range(self.world):
+            if q == self.rank:
+                flag_ptrs.append(self.flags)
+                continue
+            ptrs = [ctx.ipc_open(h) for h in everyone[q]]
+            self.opened += ptrs
+            for k in range(depth):
+                self.peer_bufs[k].append(ptrs[k])
+            flag_ptrs.append(ptrs[depth])
+        ctx.set_flag_peers(flag_ptrs, self.rank)
+        self.views = [torch.as_tensor(_DevView(p, max(self.slot_bytes, 16)), device=device)[: self.slot_bytes]
+                      .view(self.world * n_local, n_models, 16) for p in self.bufs]
+        self.i = 0
+        if self.world > 1:
+            dist.barrier()          # every rank has opened every handle before anyone publishes
+
+    def local_buffer(self):
+        k = self.i % self.depth
+        self.ctx.set_hit_peers(self.peer_bufs[k], first_record=self.rank * self.n_local)
+        return self.views[k][self.rank * self.n_local:(self.rank + 1) * self.n_local]
+
+    def submit(self):
+        k = self.i % self.depth
+        self.i += 1
+        self.ctx.peer_signal(self.i)
+        return self.views[k]
+
+    def wait(self, step: int):
+        """Stream-ordered: what follows on the stream sees every rank's records of step `step` (1-based)."""
+        self.ctx.peer_wait(step)
+
+    def drain(self):
+        if self.i:
+            self.ctx.peer_wait(self.i)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        self.ctx.set_hit_peers([], 0)
+        self.ctx.set_flag_peers([], 0)
+        torch.cuda.synchronize()
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier()          # nobody unmaps a buffer a peer may still be writing
+        self.views = []
+        for p in self.opened:
+            self.ctx.ipc_close(p)
+        self.opened = []
+        for p in self.bufs + [self.flags]:
+            self.ctx.device_free(p)
+        self.bufs = []

@@ -41,6 +41,36 @@ WORKER = textwrap.dedent("""
         torch.cuda.synchronize()
         assert full.shape == one.shape and torch.equal(full, one), "sharded result differs from single-GPU result"
     dist.barrier()
+
+    # ---- the same through PeerGather: the producing kernels store every record into every rank's buffer (P2P) ----
+    from squigglekit_b200.dist import PeerGather
+    n_even = 1000
+    per = n_even // world
+    pg = PeerGather(ctx, per, 1, torch.device("cuda", local), depth=2)
+    for step in range(3):                                  # three steps: both buffers get reused
+        out = pg.local_buffer()
+        blk = torch.from_numpy(off[rank * per:(rank + 1) * per + 1].copy()).cuda()
+        ctx.motifseq(dsig, blk, motif, scale="zscale", max_read_len=2048, out=out, want_kept=False)
+        gathered = pg.submit()
+    pg.drain()
+    torch.cuda.synchronize()
+    one, _ = ctx.motifseq(dsig, torch.from_numpy(off[:n_even + 1].copy()).cuda(), motif, scale="zscale", max_read_len=2048)
+    torch.cuda.synchronize()
+    assert torch.equal(gathered, one), f"rank {rank}: records gathered over P2P differ from the single-GPU result"
+    # single-pass plan and a medmad run publish through the generic kernel / status records
+    ctx.set_dtw_plan("single_pass")
+    out = pg.local_buffer()
+    ctx.motifseq(dsig, blk, motif, scale="medmad", max_read_len=2048, out=out, want_kept=False)
+    gathered = pg.submit()
+    pg.drain()
+    torch.cuda.synchronize()
+    got = gathered.clone()
+    pg.close()                                             # turns publication off again
+    one, _ = ctx.motifseq(dsig, torch.from_numpy(off[:n_even + 1].copy()).cuda(), motif, scale="medmad", max_read_len=2048)
+    ctx.set_dtw_plan("auto")
+    torch.cuda.synchronize()
+    assert torch.equal(got, one), f"rank {rank}: single-pass / medmad records gathered over P2P differ"
+    dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
 """)
