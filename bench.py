@@ -379,6 +379,7 @@ def main():
                     help="multi-GPU gather of the hit records: p2p = the producing kernels store every record into every peer's "
                          "buffer over NVLink (no collective kernel); nccl = all_gather_into_tensor; none = no exchange (experiments)")
     ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: host threads (default: all hardware threads, ignoring OMP_NUM_THREADS)")
+    ap.add_argument("--seed-offset", type=int, default=0, help="added to the per-rank data seed (reproduce another rank's batch on one GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (very large batches: they need the batch in host memory)")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained twin, the segmenter block and the CLI block")
@@ -417,7 +418,7 @@ def main():
     if args.lanes:
         ctx.set_dtw_lanes(args.lanes)
     ctx.set_dtw_plan(args.plan)
-    sig = synth.motifseq_reads_torch(R, M, motif, dev, seed=synth.BASE_SEED + rank).view(-1)
+    sig = synth.motifseq_reads_torch(R, M, motif, dev, seed=synth.BASE_SEED + rank + args.seed_offset).view(-1)
     off = torch.arange(R + 1, dtype=torch.int64, device=dev) * M
     exchange = args.exchange
     if exchange == "auto":

@@ -188,6 +188,31 @@ SQK_API int sqk_adapter(sqk_ctx *ctx, const int16_t *signals, const int64_t *off
                         int64_t max_read_len, const sqk_adapter_params *params, int mem, int32_t *segs, int32_t *found);
 
 /* ---------------------------------------------------------------------------------------
+ * The rolling-mean adapter finder of dRNA_segmenter.py's TSV branch (dRNA_segmenter.py:272-326):
+ *   scale_outliers (lim_lo < s < lim_hi, :278, :331-334) -> t = pd.Series(sig).rolling(window=w).mean() (:281-282)
+ *   -> bot = t.mean() - t.std() * std_factor (:283-287, pandas nanops: NaN slots skipped, ddof = 1)
+ *   -> runs of t < bot closed by t > bot, merged when closer than seg_dist (:291-313)
+ *   -> the first segment with lo_thresh <= end - start <= hi_thresh, printed as (start - shift, end - shift) (:315-323).
+ * As shipped the branch raises NameError: `w` only exists in the comment `# w = 2000` (:81); it is a parameter here.
+ * segs[r] = (start - shift, end - shift), found[r] = 1, or (0, 0) and 0.  max_read_len as for sqk_segmenter.
+ * w must be in [1, 65536].
+ * ------------------------------------------------------------------------------------- */
+typedef struct sqk_rollmean_params {
+    int32_t w;              /* 2000   :81  */
+    int32_t seg_dist;       /* 1500   :292 */
+    int32_t lo_thresh;      /* 2000   :294 */
+    int32_t hi_thresh;      /* 200000 :293 */
+    int32_t shift;          /* 1000   :320 */
+    int32_t lim_lo, lim_hi; /* 0, 1200 :333 */
+    int32_t reserved;
+    double std_factor;      /* 0.5    :287 */
+} sqk_rollmean_params;
+#define SQK_ROLLMEAN_DEFAULTS {2000, 1500, 2000, 200000, 1000, 0, 1200, 0, 0.5}
+
+SQK_API int sqk_rollmean(sqk_ctx *ctx, const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                         int64_t max_read_len, const sqk_rollmean_params *params, int mem, int32_t *segs, int32_t *found);
+
+/* ---------------------------------------------------------------------------------------
  * float64 signals.  The reference's `-s` path hands both tools whatever the TSV holds (MotifSeq.py:270
  * `float(i) for i in l[8:]`; segmenter.py:198-199), e.g. SquigglePull's pA output.  Same semantics and outputs as
  * sqk_motifseq / sqk_segmenter with `signals` as float64: outlier window, numpy-exact float statistics (pairwise

@@ -10,6 +10,7 @@ container; the DTW is a restatement of un-vendored mlpy 3.5.0 -> "parity unpinne
 """
 from .cpu import (  # noqa: F401
     AdapterCfg,
+    RollmeanCfg,
     SegCfg,
     adapter_batch,
     adapter_seg,
@@ -25,6 +26,8 @@ from .cpu import (  # noqa: F401
     motifseq_batch_f64,
     np_median,
     np_sum,
+    rollmean_batch,
+    rollmean_seg,
     segmenter_batch,
     segmenter_batch_pa,
     segmenter_batch_f64,

@@ -76,6 +76,25 @@ class AdapterCfg:
                            self.t_end, self.std_scale)
 
 
+class _RollmeanCfg(C.Structure):
+    _fields_ = [("w", C.c_int32), ("seg_dist", C.c_int32), ("lo_thresh", C.c_int32), ("hi_thresh", C.c_int32),
+                ("shift", C.c_int32), ("std_factor", C.c_double)]
+
+
+@dataclass
+class RollmeanCfg:
+    """The constants of the TSV branch of dRNA_segmenter.py (:81 `# w = 2000`, :287, :292-294, :320)."""
+    w: int = 2000
+    seg_dist: int = 1500
+    lo_thresh: int = 2000
+    hi_thresh: int = 200000
+    shift: int = 1000
+    std_factor: float = 0.5
+
+    def c(self) -> _RollmeanCfg:
+        return _RollmeanCfg(self.w, self.seg_dist, self.lo_thresh, self.hi_thresh, self.shift, self.std_factor)
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
@@ -105,6 +124,8 @@ def lib() -> C.CDLL:
                                               C.c_int, ip, ip]
         L.orc_adapter_seg.argtypes = [dp, C.c_int64, C.POINTER(_AdapterCfg), ip, dp]
         L.orc_adapter_batch.argtypes = [C.c_void_p, lp, C.c_int64, C.POINTER(_AdapterCfg), C.c_int, C.c_int, C.c_int, ip, ip]
+        L.orc_rollmean_seg.argtypes = [dp, C.c_int64, C.POINTER(_RollmeanCfg), ip, dp]
+        L.orc_rollmean_batch.argtypes = [C.c_void_p, lp, C.c_int64, C.POINTER(_RollmeanCfg), C.c_int, C.c_int, C.c_int, ip, ip]
         _lib = L
     return _lib
 
@@ -309,4 +330,32 @@ def adapter_batch(signals, offsets, cfg: AdapterCfg = AdapterCfg(), lim_lo=0, li
     rc = lib().orc_adapter_batch(signals.ctypes.data, _lp(offsets), n, C.byref(c), lim_lo, lim_hi, n_threads, _ip(segs), _ip(found))
     if rc:
         raise RuntimeError("orc_adapter_batch failed")
+    return segs, found
+
+
+def rollmean_seg(sig, cfg: RollmeanCfg = RollmeanCfg(), want_thresholds: bool = False):
+    """dRNA_segmenter.py TSV branch (:272-326) on one post-outlier signal -> [x, y] of the first qualifying segment
+    (already shifted by -1000 as the reference prints it) or None."""
+    v = np.ascontiguousarray(sig, dtype=np.float64)
+    out = np.zeros(2, dtype=np.int32)
+    thr = np.zeros(3, dtype=np.float64)
+    c = cfg.c()
+    got = lib().orc_rollmean_seg(_dp(v), v.size, C.byref(c), _ip(out), _dp(thr))
+    if got < 0:
+        raise RuntimeError("orc_rollmean_seg failed")
+    seg = [int(out[0]), int(out[1])] if got else None
+    return (seg, thr) if want_thresholds else seg
+
+
+def rollmean_batch(signals, offsets, cfg: RollmeanCfg = RollmeanCfg(), lim_lo=0, lim_hi=1200, n_threads=0):
+    """Per read: scale_outliers -> rollmean_seg.  -> (segs[n,2], found[n])."""
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    segs = np.zeros((n, 2), dtype=np.int32)
+    found = np.zeros(n, dtype=np.int32)
+    c = cfg.c()
+    rc = lib().orc_rollmean_batch(signals.ctypes.data, _lp(offsets), n, C.byref(c), lim_lo, lim_hi, n_threads, _ip(segs), _ip(found))
+    if rc:
+        raise RuntimeError("orc_rollmean_batch failed")
     return segs, found

@@ -466,6 +466,146 @@ ORC_API int orc_adapter_batch(const int16_t *signals, const int64_t *offsets, in
 }
 
 /* ------------------------------------------------------------------------------------
+ * dRNA_segmenter.py, TSV branch (dRNA_segmenter.py:272-326): the rolling-mean adapter finder.  sig is the
+ * post-outlier signal (scale_outliers (0, 1200), :331-334).  As shipped the branch raises NameError (`w` is only
+ * defined in a comment, :81 "# w = 2000"); w is a parameter here, default 2000 as that comment says.
+ *   t   = pd.Series(sig).rolling(window=w).mean()     (:281-282)  pandas 3.0 roll_mean (aggregations.pyx): the first
+ *         w-1 outputs are NaN; sum_x is kept by Kahan-compensated add (compensation_add) / remove (compensation_remove)
+ *         per step, output sum_x / nobs; when the last nobs values were identical the output is that value; a negative
+ *         result over all-non-negative values is clamped to 0 (and vice versa).
+ *   mn  = t.mean()  -> nanops.nanmean: NaN -> 0, numpy pairwise sum over ALL n slots, divided by the count of non-NaN
+ *   std = t.std()   -> nanops.nanvar(ddof=1): avg as above; sqr = (avg - t)**2 with NaN slots set to 0; pairwise sum
+ *         over all n slots / (count - 1); sqrt.  count <= 1 -> NaN.
+ *   bot = mn - std * std_factor                        (:287, std_factor = 0.5)
+ *   run detector :291-313 (comparisons with NaN are False; a value equal to bot does nothing; a run with a single
+ *   sample below keeps end = 0; no flush at the end), merge rule with seg_dist, then the first segment with
+ *   lo_thresh <= b - a <= hi_thresh is printed as (a - shift, b - shift) (:315-323).
+ * Returns 1 and writes out[0..1], else 0.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t w, seg_dist, lo_thresh, hi_thresh, shift;
+    double std_factor;
+} orc_rollmean_cfg;
+
+/* pandas roll_mean, fixed window w, min_periods = w; out[i] for i < n */
+static void pd_roll_mean(const double *v, int64_t n, int64_t w, double *out)
+{
+    double sum_x = 0.0, comp_add = 0.0, comp_rem = 0.0, prev_value = n > 0 ? v[0] : 0.0;
+    int64_t nobs = 0, neg_ct = 0, same = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (i >= w) {                                         /* remove_mean(v[i - w]) */
+            const double val = v[i - w];
+            if (val == val) {
+                nobs--;
+                const double y = -val - comp_rem;
+                const double t = sum_x + y;
+                comp_rem = t - sum_x - y;
+                sum_x = t;
+                if (signbit(val)) neg_ct--;
+            }
+        }
+        {                                                     /* add_mean(v[i]) */
+            const double val = v[i];
+            if (val == val) {
+                nobs++;
+                const double y = val - comp_add;
+                const double t = sum_x + y;
+                comp_add = t - sum_x - y;
+                sum_x = t;
+                if (signbit(val)) neg_ct++;
+                if (val == prev_value) same++; else same = 1;
+                prev_value = val;
+            }
+        }
+        double r = NAN;                                       /* calc_mean, minp = w */
+        if (nobs >= w && nobs > 0) {
+            r = sum_x / (double)nobs;
+            if (same >= nobs) r = prev_value;
+            else if (neg_ct == 0 && r < 0) r = 0;
+            else if (neg_ct == nobs && r > 0) r = 0;
+        }
+        out[i] = r;
+    }
+}
+
+ORC_API int orc_rollmean_seg(const double *sig, int64_t n, const orc_rollmean_cfg *cfg, int32_t *out,
+                             double *thr /* bot, mn, std or NULL */)
+{
+    double bot = NAN, mn = NAN, sd = NAN;
+    double *t = (double *)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    double *z = (double *)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    if (!t || !z) { free(t); free(z); return -1; }
+    pd_roll_mean(sig, n, cfg->w, t);
+    int64_t count = 0;
+    for (int64_t i = 0; i < n; i++) { const int ok = t[i] == t[i]; count += ok; z[i] = ok ? t[i] : 0.0; }
+    if (count > 0) {
+        mn = np_pairwise(z, n) / (double)count;
+        if (count > 1) {
+            for (int64_t i = 0; i < n; i++) { const double d = mn - z[i]; z[i] = (t[i] == t[i]) ? d * d : 0.0; }
+            sd = sqrt(np_pairwise(z, n) / (double)(count - 1));
+        }
+    }
+    bot = mn - sd * cfg->std_factor;
+    if (thr) { thr[0] = bot; thr[1] = mn; thr[2] = sd; }
+
+    int begin = 0, have_last = 0, found = 0;
+    int64_t start = 0, end = 0, last_a = 0, last_b = 0;
+    for (int64_t i = 0; i <= n && !found; i++) {
+        int close = 0;
+        if (i < n) {
+            const double x = t[i];
+            if (x < bot && !begin) { start = i; begin = 1; }
+            else if (x < bot) end = i;
+            else if (x > bot && begin) close = 1;
+        }
+        /* a list entry is final once the next one is appended (or at the end of the read): test it then */
+        const int append = close && !(have_last && start - last_b < cfg->seg_dist);
+        if ((append || i == n) && have_last) {
+            const int64_t d = last_b - last_a;
+            if (!(d > cfg->hi_thresh) && !(d < cfg->lo_thresh)) {
+                out[0] = (int32_t)(last_a - cfg->shift); out[1] = (int32_t)(last_b - cfg->shift); found = 1;
+            }
+        }
+        if (close) {
+            if (append) { last_a = start; last_b = end; have_last = 1; }
+            else last_b = end;
+            start = 0; end = 0; begin = 0;
+        }
+    }
+    free(t); free(z);
+    return found;
+}
+
+/* per read: scale_outliers (lim_lo, lim_hi) -> orc_rollmean_seg.  found[r] = 1/0, segs[r] = (x, y). */
+ORC_API int orc_rollmean_batch(const int16_t *signals, const int64_t *offsets, int64_t n_reads,
+                               const orc_rollmean_cfg *cfg, int lim_lo, int lim_hi, int n_threads,
+                               int32_t *segs, int32_t *found)
+{
+    int failed = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        int got = 0;
+        segs[2 * r] = 0; segs[2 * r + 1] = 0;
+        if (len > 0) {
+            double *y = (double *)malloc((size_t)len * sizeof(double));
+            if (!y) failed = 1;
+            else {
+                const int64_t kept = orc_scale_outliers_i16(signals + offsets[r], len, lim_lo, lim_hi, y);
+                got = orc_rollmean_seg(y, kept, cfg, segs + 2 * r, NULL);
+                if (got < 0) { failed = 1; got = 0; }
+                free(y);
+            }
+        }
+        found[r] = got;
+    }
+    return failed ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Batch drivers (OpenMP over reads) -- the "reference arm" / cpu_baseline of bench.py and
  * the large-set parity checker.  Per read they do exactly what the reference's main loop
  * does: scale_outliers -> normalise -> dtw_subsequence -> (start,end,dist).

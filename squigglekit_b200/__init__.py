@@ -8,6 +8,7 @@ B200.
 from .core import (  # noqa: F401
     AdapterConfig,
     Context,
+    RollmeanConfig,
     SegConfig,
     SqkError,
     HIT_DTYPE,

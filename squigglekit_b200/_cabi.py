@@ -46,6 +46,12 @@ class AdapterParams(C.Structure):
                 ("lim_lo", C.c_int32), ("lim_hi", C.c_int32)]
 
 
+class RollmeanParams(C.Structure):
+    _fields_ = [("w", C.c_int32), ("seg_dist", C.c_int32), ("lo_thresh", C.c_int32), ("hi_thresh", C.c_int32),
+                ("shift", C.c_int32), ("lim_lo", C.c_int32), ("lim_hi", C.c_int32), ("reserved", C.c_int32),
+                ("std_factor", C.c_double)]
+
+
 class Timing(C.Structure):
     _fields_ = [("launches", C.c_int64 * K_COUNT), ("ms", C.c_double * K_COUNT)]
 
@@ -55,7 +61,7 @@ EXPORTS = [
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
     "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
     "sqk_ctx_get_launches", "sqk_ctx_set_stats_generation", "sqk_device_alloc", "sqk_device_free", "sqk_ipc_export", "sqk_ipc_open",
-    "sqk_ipc_close", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
+    "sqk_ipc_close", "sqk_rollmean", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
 ]
 
 _lib = None
@@ -87,6 +93,7 @@ def lib() -> C.CDLL:
     L.sqk_motifseq_trace.argtypes = [vp, vp, i64, vp, i32, C.POINTER(MotifParams), vp, vp, i64, C.POINTER(i64), vp]
     L.sqk_segmenter.argtypes = [vp, vp, vp, i64, i64, C.POINTER(SegParams), C.c_int, vp, vp]
     L.sqk_adapter.argtypes = [vp, vp, vp, i64, i64, C.POINTER(AdapterParams), C.c_int, vp, vp]
+    L.sqk_rollmean.argtypes = [vp, vp, vp, i64, i64, C.POINTER(RollmeanParams), C.c_int, vp, vp]
     L.sqk_segmenter_pa.argtypes = [vp, vp, vp, i64, i64, vp, vp, C.POINTER(SegParams), C.c_int, vp, vp]
     L.sqk_motifseq_f64.argtypes = [vp, vp, vp, i64, vp, vp, i32, C.POINTER(MotifParams), C.c_int, vp, vp]
     L.sqk_segmenter_f64.argtypes = [vp, vp, vp, i64, C.POINTER(SegParams), C.c_int, vp, vp]

@@ -1,12 +1,12 @@
-"""Drop-in command line for the slow5 branch of the reference's dRNA_segmenter.py: ``-f/--slow5 file.blow5`` in,
-``readID<TAB>start<TAB>end`` of the adapter segment out (dRNA_segmenter.py:86-176); reads without a segment print
-nothing, as in the reference.  The whole per-read computation (outlier removal, threshold statistics over samples
-[1000, 5000), the run detector) runs in libsqk on the GPU, batched.
+"""Drop-in command line for the reference's dRNA_segmenter.py.
 
-Differences, all loud:
-  * ``-s/--signal`` (the TSV branch, dRNA_segmenter.py:272-326) cannot run in the reference as shipped (``w`` is
-    undefined, NameError) and is not provided -> error message.
-  * ``-p`` plotting is out of scope -> warning.
+``-f/--slow5 file.blow5``: ``readID<TAB>start<TAB>end`` of the adapter segment (dRNA_segmenter.py:86-176: outlier
+removal, threshold statistics over samples [1000, 5000), one-sided run detector).
+``-s/--signal file.tsv``: ``fast5<TAB>readID<TAB>start<TAB>end`` from the rolling-mean detector (dRNA_segmenter.py:272-326:
+``rolling(window=w).mean()``, ``bot = mean - 0.5 std``, runs below ``bot``).  As shipped that branch raises NameError
+(``w`` only exists in the comment ``# w = 2000``, :81); here ``w`` defaults to 2000 and ``--window`` changes it.
+Reads without a segment print nothing, as in the reference.  The whole per-read computation runs in libsqk on the GPU,
+batched.  ``-p`` plotting is out of scope -> warning.
 """
 from __future__ import annotations
 
@@ -32,6 +32,8 @@ def build_parser():
     parser.add_argument("-f", "--slow5", help="slow5 file")
     parser.add_argument("-c", "--start_col", type=int, default="4", help="start column for signal")
     parser.add_argument("-p", "--plot", action="store_true", help="Live plot each segment")
+    parser.add_argument("--window", type=int, default=2000,
+                        help="rolling-mean window of the -s branch (the reference's `# w = 2000`)")
     return parser
 
 
@@ -47,6 +49,18 @@ def flush(ctx, names, sigs, out):
     names.clear(); sigs.clear()
 
 
+def flush_tsv(ctx, cfg, names, sigs, out):
+    if not names:
+        return
+    offsets = np.zeros(len(sigs) + 1, dtype=np.int64)
+    np.cumsum([s.size for s in sigs], out=offsets[1:])
+    segs, found = ctx.rollmean(np.concatenate(sigs) if offsets[-1] else np.zeros(0, np.int16), offsets, cfg)
+    for r, (f5, rid) in enumerate(names):
+        if found[r] > 0:
+            out.write("{}\t{}\t{}\t{}\n".format(f5, rid, int(segs[r, 0]), int(segs[r, 1])))
+    names.clear(); sigs.clear()
+
+
 def main(argv=None, out=sys.stdout):
     parser = build_parser()
     args = parser.parse_args(argv)
@@ -55,13 +69,25 @@ def main(argv=None, out=sys.stdout):
         sys.exit(1)
     if args.plot:
         sys.stderr.write("warning: -p plotting is not part of the B200 build; continuing without it\n")
-    if not args.slow5:
-        sys.stderr.write("error: only -f/--slow5 input is supported: the reference's -s branch uses an undefined "
-                         "window `w` (dRNA_segmenter.py:281) and cannot run as shipped\n")
-        sys.exit(2)
     import squigglekit_b200 as sqk
     from . import slow5
     names, sigs, pending = [], [], 0
+    if not args.slow5:
+        if not args.signal:
+            parser.print_help(sys.stderr)
+            sys.exit(1)
+        cfg = sqk.RollmeanConfig(w=args.window)
+        with sqk.Context(0) as ctx, open(args.signal, "rt") as fh:
+            for line in fh:
+                cols = line.rstrip("\n").split("\t")
+                # int() per field as the reference does (:278); values beyond int16 are outliers either way
+                sig = np.clip(np.array([int(v) for v in cols[args.start_col:]], dtype=np.int64), -32768, 32767).astype(np.int16)
+                names.append((cols[0], cols[1])); sigs.append(sig)
+                pending += sig.size
+                if pending >= BATCH_SAMPLES or len(names) >= BATCH_READS:
+                    flush_tsv(ctx, cfg, names, sigs, out); pending = 0
+            flush_tsv(ctx, cfg, names, sigs, out)
+        return
     with sqk.Context(0) as ctx:
         for rec in slow5.read_blow5(args.slow5):
             names.append(rec["read_id"]); sigs.append(np.ascontiguousarray(rec["signal"], dtype=np.int16))

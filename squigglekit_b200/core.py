@@ -57,6 +57,19 @@ class AdapterConfig:
     lim_hi: int = 1200
 
 
+@dataclass
+class RollmeanConfig:
+    """The constants of the TSV branch of dRNA_segmenter.py (:81 ``# w = 2000``, :287, :292-294, :320, :333)."""
+    w: int = 2000
+    seg_dist: int = 1500
+    lo_thresh: int = 2000
+    hi_thresh: int = 200000
+    shift: int = 1000
+    std_factor: float = 0.5
+    lim_low: int = 0
+    lim_hi: int = 1200
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -379,6 +392,38 @@ def _adapter(self, signals, offsets, cfg: AdapterConfig = AdapterConfig(), max_r
 
 
 Context.adapter = _adapter
+
+
+def _rollmean(self, signals, offsets, cfg: RollmeanConfig = RollmeanConfig(), max_read_len: int = 0):
+    """Batched rolling-mean adapter finder (dRNA_segmenter.py:272-326, TSV branch): per read scale_outliers,
+    t = rolling(w).mean(), bot = t.mean() - std_factor * t.std(), runs of t < bot, first segment of a plausible length.
+
+    -> (segs int32 [n_reads, 2] = (start - shift, end - shift), found int32 [n_reads]); found == 0: the reference prints
+    nothing for that read."""
+    p = _cabi.RollmeanParams(cfg.w, cfg.seg_dist, cfg.lo_thresh, cfg.hi_thresh, cfg.shift, cfg.lim_low, cfg.lim_hi, 0,
+                             cfg.std_factor)
+    if _is_torch(signals):
+        import torch
+        if signals.dtype != torch.int16 or offsets.dtype != torch.int64:
+            raise TypeError("device mode needs int16 signals and int64 offsets")
+        n_reads = offsets.numel() - 1
+        segs = torch.zeros((n_reads, 2), dtype=torch.int32, device=signals.device)
+        found = torch.zeros(n_reads, dtype=torch.int32, device=signals.device)
+        self._use_torch_stream()
+        _cabi.check(self._lib.sqk_rollmean(self._h, signals.data_ptr(), offsets.data_ptr(), n_reads, int(max_read_len),
+                                           C.byref(p), _cabi.SQK_MEM_DEVICE, segs.data_ptr(), found.data_ptr()))
+        return segs, found
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n_reads = offsets.size - 1
+    segs = np.zeros((n_reads, 2), dtype=np.int32)
+    found = np.zeros(n_reads, dtype=np.int32)
+    _cabi.check(self._lib.sqk_rollmean(self._h, signals.ctypes.data, offsets.ctypes.data, n_reads, int(max_read_len),
+                                       C.byref(p), _cabi.SQK_MEM_HOST, segs.ctypes.data, found.ctypes.data))
+    return segs, found
+
+
+Context.rollmean = _rollmean
 
 
 def hits_from_torch(hits_u8) -> np.ndarray:

@@ -19,6 +19,8 @@
 #include "sqk_f64.cuh"
 #include "sqk_stats.cuh"
 #include "sqk_stats2.cuh"
+#include "sqk_stats3.cuh"
+#include "sqk_rollmean.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -100,7 +102,7 @@ struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
-    DevBuf redo, mask;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
+    DevBuf redo, mask, rm_p, rm_masks;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -159,6 +161,7 @@ struct sqk_ctx {
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1, stats_smem_set256 = -1;
     int stats2_smem_set[5] = {-1, -1, -1, -1, -1};
+    int stats3_smem_set[3] = {-1, -1, -1};
     int stats_gen = 0;                // 0 = automatic, 1 = first-generation kernel only (experiments / tests)
     // device-mode calls share the ctx scratch in stream order: the end of every enqueue is marked with an event and a
     // call that arrives on a different stream waits for it first
@@ -485,6 +488,57 @@ static int launch_stats2(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, con
     return rc;
 }
 
+// K1, third generation (sqk_stats3.cuh): one warp per read, for the zscale / segmenter (raw integer) / none modes; the
+// reads it hands back are worked off by the first-generation kernel through the redo list.
+static int launch_stats3(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, const View &v, bool want_mask, StatsOut *so)
+{
+    Stats3Args A{};
+    const int cap_units = (int)((std::max<int64_t>(v.max_len, 8) + 14 + 7) / 8);
+    A.buf_bytes = ((cap_units + 15) / 16) * 256;
+    const int lo1 = std::max(a.lo + 1, -32768), hi1 = std::min(a.hi - 1, 32767);
+    const int nbins = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
+    A.hist_words = a.mode == SQK_STATS_SEGMENTER ? std::max(128, (nbins + 127) & ~127) : 0;
+    A.mask_words = want_mask ? ((A.buf_bytes / 64 + 2 + 3) & ~3) : 0;
+    A.mask_stride = 0;
+    if (want_mask) {
+        A.mask_stride = (int)((((v.max_len + 31) / 32) + 3) & ~3ll);
+        if (A.mask_stride < 4) A.mask_stride = 4;
+        TRY(ensure(s.mask, (size_t)v.n_reads * A.mask_stride * sizeof(uint32_t)));
+        A.mask = (uint32_t *)s.mask.p;
+    }
+    TRY(ensure(s.redo, ((size_t)v.n_reads + 4) * sizeof(int)));
+    A.n_redo = (unsigned *)s.redo.p;
+    A.redo = (int *)s.redo.p + 4;
+    CU(cudaMemsetAsync(s.redo.p, 0, 16, st));
+    const int dyn = (int)sqk_s3_smem_bytes(A);
+    void (*kern)(const Stats3Args) = nullptr;
+    int which = 0;
+    switch (a.mode) {
+    case SQK_STATS_ZSCALE: kern = sqk_stats3_kernel<SQK_STATS_ZSCALE>; which = 0; break;
+    case SQK_STATS_NONE: kern = sqk_stats3_kernel<SQK_STATS_NONE>; which = 1; break;
+    default: kern = sqk_stats3_kernel<SQK_STATS_SEGMENTER>; which = 2; break;
+    }
+    if (dyn > c->stats3_smem_set[which]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        c->stats3_smem_set[which] = dyn;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, dyn));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * per_sm));
+    A.s = a;
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_STATS, st, &eb));
+    kern<<<(unsigned)grid, 32, dyn, st>>>(A);
+    CU(cudaGetLastError());
+    c->n_launches++;
+    a.list = A.redo; a.n_list = A.n_redo; a.extra_flags = SQK_FLAG_NO_MASK;
+    so->v2 = true; so->redo = A.redo; so->n_redo = A.n_redo; so->mask = A.mask; so->mask_stride = A.mask_stride;
+    const int rc = launch_stats_nt<128>(c, s, st, a, v, &c->stats_smem_set128, /*timed=*/false, /*max_grid=*/c->n_sms);
+    TRY(tock(eb, st));
+    return rc;
+}
+
 static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int mode, int lo, int hi, int num,
                         double std_scale, int32_t *d_nkept, const double *d_pa_off = nullptr,
                         const double *d_pa_scale = nullptr, int t_start = 0, int t_end = 0, StatsOut *so = nullptr,
@@ -503,8 +557,14 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     if (env_gen < 0) { const char *e = getenv("SQK_STATS_GEN"); env_gen = e ? atoi(e) : 0; }   // experiments: 1 = first generation only
     const int gen = c->stats_gen ? c->stats_gen : env_gen;
     StatsOut local;
-    if (gen != 1 && mode != SQK_STATS_ADAPTER && v.max_len <= SQK_S2_MAX_LEN && v.n_reads < 0x7ffffff0LL)
+    if (gen != 1 && mode != SQK_STATS_ADAPTER && v.max_len <= SQK_S2_MAX_LEN && v.n_reads < 0x7ffffff0LL) {
+        // third generation (one warp per read) where it applies: raw-integer zscale / segmenter / none, histogram-sized window
+        const bool s3_mode = mode == SQK_STATS_ZSCALE || mode == SQK_STATS_NONE || (mode == SQK_STATS_SEGMENTER && d_pa_off == nullptr);
+        const int64_t span = (int64_t)std::min(hi - 1, 32767) - std::max(lo + 1, -32768) + 1;
+        if (gen != 2 && s3_mode && (mode != SQK_STATS_SEGMENTER || span <= SQK_S3_MAX_BINS))
+            return launch_stats3(c, s, st, a, v, want_mask, so ? so : &local);
         return launch_stats2(c, s, st, a, v, want_mask, so ? so : &local);
+    }
     // one CTA per read; the warp-per-read form (SQK_STATS_NT=32, reads <= 8192 samples) is kept for experiments
     static int force_nt = -1;
     if (force_nt < 0) { const char *e = getenv("SQK_STATS_NT"); force_nt = e ? atoi(e) : 0; }
@@ -614,7 +674,7 @@ static int check_motif_params(const sqk_motif_params *p)
     return SQK_OK;
 }
 
-#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head
+#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head, [5] #long window jobs
 
 // stats + the DTW of every model over a device-resident View; d_hits is [n_reads][n_models]
 static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
@@ -676,11 +736,13 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         b.hits = a.hits; b.hit_stride = a.hit_stride;
         b.counter = ctr;
         b.jobs = (DtwJob *)s.jobs.p; b.n_jobs = ctr + 1;
+        b.n_long = ctr + 5; b.jobs_cap = (int)(v.n_reads * SQK_LB_MAX_CLUSTERS);
         b.reads = (LbRead *)s.lbreads.p;
         b.xmax_abs = xmax;
         b.W = sqk_lb_window(N);
         if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the fallback
         b.short_len = 2 * (b.W + N);
+        b.long_cols = 4 * (b.W + N);             // a typical window job is W + 1 + a few columns
         TRY(tick(c, SQK_K_DTW_LB, st, &eb));
         cudaError_t e = pick_lb(LL)(LK, b, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW lower-bound launch (N=%d, K=%d, L=%d): %s", N, LK, LL, cudaGetErrorString(e));
@@ -688,7 +750,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
 
         TRY(tick(c, SQK_K_DTW_WIN, st, &eb));
         a.counter = ctr + 2;
-        a.jobs = b.jobs; a.n_jobs = ctr + 1;
+        a.jobs = b.jobs; a.n_jobs = ctr + 1; a.n_long = ctr + 5; a.jobs_cap = b.jobs_cap;
         a.job_out = (sqk_hit *)s.jobres.p; a.job_out_stride = 1;
         e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW window launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
@@ -701,7 +763,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         sqk_dtw_finalize_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(f);
         CU(cudaGetLastError());
         a.counter = ctr + 4;
-        a.jobs = f.fb_jobs; a.n_jobs = ctr + 3;
+        a.jobs = f.fb_jobs; a.n_jobs = ctr + 3; a.n_long = nullptr; a.jobs_cap = 0;
         a.job_out = a.hits; a.job_out_stride = a.hit_stride;
         e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
@@ -792,6 +854,49 @@ static int enqueue_adapter(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, 
     cudaEvent_t eb;
     TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
     sqk_adapter_fsm_kernel<<<grid, SQK_ADAPTER_THREADS, 0, st>>>(a);
+    CU(cudaGetLastError());
+    c->n_launches++;
+    TRY(tock(eb, st));
+    return SQK_OK;
+}
+
+static int check_rollmean_params(const sqk_rollmean_params *p)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    if (p->w < 1 || p->w > 65536) return fail(SQK_ERR_ARG, "w must be in [1, 65536]");
+    return SQK_OK;
+}
+
+// dRNA rolling-mean adapter finder (sqk_rollmean.cuh): one kernel, one CTA per read
+static int enqueue_rollmean(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const sqk_rollmean_params *p,
+                            int32_t *d_segs, int32_t *d_found)
+{
+    if (v.n_reads == 0) return SQK_OK;
+    if (v.n_reads > 0x7fffffffLL) return fail(SQK_ERR_ARG, "more than 2^31-1 reads in one launch");
+    if (v.max_len > 0x7ffffff0LL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-16 samples");
+    const int dyn = (int)((sizeof(RmShared) + 15) & ~(size_t)15);
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sqk_rollmean_kernel, SQK_RM_THREADS, dyn));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t p_stride = ((v.max_len + 1 + 31) & ~31ll), m_stride = ((v.max_len + 31) / 32 + 2 + 7) & ~7ll;
+    // scratch per CTA: 4 bytes per sample (prefix sums) + two bit masks; keep the whole at <= 2 GiB
+    const int64_t per_cta = 4 * p_stride + 8 * m_stride;
+    int64_t grid = std::min<int64_t>(v.n_reads, (int64_t)c->n_sms * per_sm);
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, (2ll << 30) / per_cta));
+    TRY(ensure(s.rm_p, (size_t)grid * p_stride * sizeof(int32_t)));
+    TRY(ensure(s.rm_masks, (size_t)grid * 2 * m_stride * sizeof(uint32_t)));
+    RollmeanArgs a{};
+    a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+    a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
+    a.lo = clamp_lim(p->lim_lo); a.hi = clamp_lim(p->lim_hi);
+    a.w = p->w; a.seg_dist = p->seg_dist; a.lo_thresh = p->lo_thresh; a.hi_thresh = p->hi_thresh; a.shift = p->shift;
+    a.std_factor = p->std_factor;
+    a.P = (int32_t *)s.rm_p.p; a.p_stride = p_stride;
+    a.masks = (uint32_t *)s.rm_masks.p; a.m_stride = m_stride;
+    a.segs = d_segs; a.found = d_found;
+    cudaEvent_t eb;
+    TRY(tick(c, SQK_K_SEG_FSM, st, &eb));
+    sqk_rollmean_kernel<<<(unsigned)grid, SQK_RM_THREADS, dyn, st>>>(a);
     CU(cudaGetLastError());
     c->n_launches++;
     TRY(tock(eb, st));
@@ -1016,7 +1121,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
     for (int i = 0; i < 2; i++) {
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
-        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks);
         release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres); release(s.redo); release(s.mask);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -1120,7 +1225,7 @@ int sqk_ctx_get_plan_counters(sqk_ctx *c, int64_t out[2])
     CU(cudaStreamSynchronize(c->slot[0].stream));
     unsigned h[SQK_CTRS_PER_MODEL];
     CU(cudaMemcpy(h, c->slot[0].counter.p, sizeof(h), cudaMemcpyDeviceToHost));
-    out[0] = h[1]; out[1] = h[3];
+    out[0] = (int64_t)h[1] + h[5]; out[1] = h[3];
     return SQK_OK;
 }
 
@@ -1333,7 +1438,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
 
 static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
                           const double *pa_offset, const double *pa_scale, const sqk_seg_params *p, int mem, int32_t *segs,
-                          int32_t *n_segs, const sqk_adapter_params *ap = nullptr)
+                          int32_t *n_segs, const sqk_adapter_params *ap = nullptr, const sqk_rollmean_params *rp = nullptr)
 {
     if ((pa_offset == nullptr) != (pa_scale == nullptr)) return fail(SQK_ERR_ARG, "pa_offset and pa_scale must be given together");
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
@@ -1341,11 +1446,12 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     if (n_reads == 0) return SQK_OK;
     if (!offsets || !segs || !n_segs) return fail(SQK_ERR_ARG, "offsets/segs/n_segs is NULL");
     if (mem != SQK_MEM_HOST && mem != SQK_MEM_DEVICE) return fail(SQK_ERR_ARG, "mem must be SQK_MEM_HOST or SQK_MEM_DEVICE");
-    if (ap) TRY(check_adapter_params(ap));      // adapter mode: one (start, end) row per read, n_segs = found flag
+    if (ap) TRY(check_adapter_params(ap));      // adapter modes: one (start, end) row per read, n_segs = found flag
+    else if (rp) TRY(check_rollmean_params(rp));
     else TRY(check_seg_params(p));
     Guard g(c->device);
     if (!g.ok) return fail(SQK_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
-    const size_t seg_row = (size_t)(ap ? 1 : p->max_segs) * 2 * sizeof(int32_t);
+    const size_t seg_row = (size_t)((ap || rp) ? 1 : p->max_segs) * 2 * sizeof(int32_t);
 
     if (mem == SQK_MEM_DEVICE) {
         cudaStream_t st = device_stream(c);
@@ -1355,6 +1461,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
         int rc;
         if (ap) rc = enqueue_adapter(c, c->slot[0], st, v, ap, segs, n_segs);
+        else if (rp) rc = enqueue_rollmean(c, c->slot[0], st, v, rp, segs, n_segs);
         else rc = enqueue_segmenter(c, c->slot[0], st, v, p, segs, n_segs, pa_offset, pa_scale);
         TRY(dev_end(c, st));
         return rc;
@@ -1396,6 +1503,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
         }
         View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
         if (ap) TRY(enqueue_adapter(c, s, st, v, ap, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
+        else if (rp) TRY(enqueue_rollmean(c, s, st, v, rp, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p));
         else TRY(enqueue_segmenter(c, s, st, v, p, (int32_t *)s.segs.p, (int32_t *)s.nsegs.p, d_po, d_ps));
         TRY(result_to_host(s, 0, (char *)segs + (size_t)r0 * seg_row, s.segs.p, (size_t)nr * seg_row, segs_pinned));
         TRY(result_to_host(s, 1, n_segs + r0, s.nsegs.p, (size_t)nr * sizeof(int32_t), nsegs_pinned));
@@ -1535,6 +1643,13 @@ int sqk_adapter(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int6
 {
     if (!p) return fail(SQK_ERR_ARG, "params is NULL");
     return segmenter_impl(c, signals, offsets, n_reads, max_read_len, nullptr, nullptr, nullptr, mem, segs, found, p);
+}
+
+int sqk_rollmean(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,
+                 const sqk_rollmean_params *p, int mem, int32_t *segs, int32_t *found)
+{
+    if (!p) return fail(SQK_ERR_ARG, "params is NULL");
+    return segmenter_impl(c, signals, offsets, n_reads, max_read_len, nullptr, nullptr, nullptr, mem, segs, found, nullptr, p);
 }
 
 int sqk_segmenter_pa(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int64_t n_reads, int64_t max_read_len,

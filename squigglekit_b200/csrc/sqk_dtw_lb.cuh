@@ -38,6 +38,8 @@ struct LbArgs {
     unsigned int *counter;    // work queue head, zeroed before launch
     DtwJob *jobs;             // job list (capacity n_reads * SQK_LB_MAX_CLUSTERS)
     unsigned int *n_jobs;     // its length, zeroed before launch
+    unsigned int *n_long;     // jobs of more than long_cols columns are stored from the END of the list (jobs[jobs_cap-1-i]) ...
+    int jobs_cap, long_cols;  // ... and taken FIRST by the exact kernel: a long job started last would set the launch time alone
     LbRead *reads;            // [n_reads]
     double xmax_abs;          // max |motif point|
     int W;                    // window columns in front of a cluster
@@ -262,7 +264,8 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         if (l == L - 1) {
                             DtwJob jb; jb.cursor = cursor0; jb.read = (int)idx; jb.col0 = 0; jb.n_cols = n; jb.arg_lo = 0;
                             jb.tainted = 0; jb.out = (int)idx * SQK_LB_MAX_CLUSTERS;
-                            a.jobs[atomicAdd(a.n_jobs, 1u)] = jb;
+                            if (n > a.long_cols) a.jobs[a.jobs_cap - 1 - (int)atomicAdd(a.n_long, 1u)] = jb;
+                            else a.jobs[atomicAdd(a.n_jobs, 1u)] = jb;
                             LbRead rec; rec.min_l = 0.0f; rec.thr = inf; rec.n_jobs = 1; rec.flags = 0;
                             a.reads[idx] = rec;
                         }
@@ -359,12 +362,15 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                     if (cl->tainted[q] < 0) rec.flags |= 4;   // its boundary column had already left the checkpoint ring
                 if (rec.flags == 0) {
                     const int nj = cl->n;
-                    const unsigned at = atomicAdd(a.n_jobs, (unsigned)nj);
+                    int n_short = 0;
+                    for (int q = 0; q < nj; q++) n_short += (cl->hi[q] - cl->col0[q] + 1 > a.long_cols) ? 0 : 1;
+                    unsigned at = n_short ? atomicAdd(a.n_jobs, (unsigned)n_short) : 0u;
                     for (int q = 0; q < nj; q++) {
                         DtwJob jb;
                         jb.cursor = cl->cursor[q]; jb.read = my_read; jb.col0 = cl->col0[q]; jb.n_cols = cl->hi[q] - cl->col0[q] + 1;
                         jb.arg_lo = cl->lo[q] - cl->col0[q]; jb.tainted = cl->tainted[q]; jb.out = my_read * SQK_LB_MAX_CLUSTERS + q;
-                        a.jobs[at + q] = jb;
+                        if (jb.n_cols > a.long_cols) a.jobs[a.jobs_cap - 1 - (int)atomicAdd(a.n_long, 1u)] = jb;   // rare
+                        else a.jobs[at++] = jb;
                     }
                     rec.n_jobs = nj;
                 }

@@ -34,3 +34,38 @@ SQK_SP_HD bool sqk_tree_leaf(int n, int depth, int j, int *off_out, int *len_out
     *off_out = off; *len_out = len;
     return !(d < depth && (j & ((1 << (depth - d)) - 1)) != 0);
 }
+
+// The same two functions with a fixed trip count (n <= 8192: at most 7 levels) and no data-dependent branch, for the
+// warp-per-read kernel (sqk_stats3.cuh); checked against the loops above for every n <= 8192 (tests/test_plan_cpu.py).
+SQK_SP_HD int sqk_tree_depth7(int n)
+{
+    int depth = 0, len = n;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int lv = 0; lv < 7; lv++) {
+        const bool go = len > 128;
+        const int half = (len >> 1) & ~7;
+        len = go ? len - half : len;
+        depth += go ? 1 : 0;
+    }
+    return depth;
+}
+
+SQK_SP_HD bool sqk_tree_leaf7(int n, int depth, int j, int *off_out, int *len_out)
+{
+    int off = 0, len = n, d = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int lv = 0; lv < 7; lv++) {
+        const bool go = len > 128;
+        const int half = (len >> 1) & ~7;
+        const bool right = ((j >> ((depth - 1 - lv) & 31)) & 1) != 0;     // (only looked at when go: then lv < depth)
+        off += (go && right) ? half : 0;
+        len = go ? (right ? len - half : half) : len;
+        d += go ? 1 : 0;
+    }
+    *off_out = off; *len_out = len;
+    return !(d < depth && (j & ((1 << (depth - d)) - 1)) != 0);
+}

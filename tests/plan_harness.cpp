@@ -191,3 +191,17 @@ double stats_tree_sum(const double *a, int n)
 }
 
 }  // extern "C"
+
+// The branch-free forms of the split rule (sqk_tree_depth7 / sqk_tree_leaf7) against the loops, every slot of the tree
+// over n elements.  -> number of disagreements.
+extern "C" int stats_tree_check7(int n)
+{
+    const int depth = sqk_tree_depth(n);
+    int bad = depth != sqk_tree_depth7(n) ? 1 : 0;
+    for (int j = 0; j < (1 << depth); j++) {
+        int o1 = 0, l1 = 0, o2 = 0, l2 = 0;
+        const bool m1 = sqk_tree_leaf(n, depth, j, &o1, &l1), m2 = sqk_tree_leaf7(n, depth, j, &o2, &l2);
+        if (m1 != m2 || (m1 && (o1 != o2 || l1 != l2))) bad++;
+    }
+    return bad;
+}

@@ -173,3 +173,46 @@ def test_adapter_oracle_matches_reference_loop(golden_dir):
     got = [[int(segs[r, 0]), int(segs[r, 1])] if found[r] else None for r in range(len(want))]
     assert got == want
     assert sum(w is not None for w in want) >= 30 and any(w is None for w in want)
+
+
+def _rollmean_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rollmean_inputs", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollmean_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_rollmean_oracle_matches_reference_loop(golden_dir):
+    """dRNA_segmenter.py's TSV-branch loop (run from the reference file, `w` injected, real pandas doing the rolling mean:
+    tests/golden/make_rollmean_golden.py) vs the C restatement on the seeded inputs, both window lengths."""
+    import json
+    want = json.load(open(os.path.join(golden_dir, "rollmean_golden.json")))
+    sig, off = _rollmean_inputs().concatenated()
+    segs, found = oracle.rollmean_batch(sig, off)
+    got = [[int(segs[r, 0]), int(segs[r, 1])] if found[r] else None for r in range(off.size - 1)]
+    assert got == want["segments"]
+    assert sum(w is not None for w in got) >= 30 and any(w is None for w in got)
+    segs, found = oracle.rollmean_batch(sig, off[:13], oracle.RollmeanCfg(w=700))
+    assert [[int(segs[r, 0]), int(segs[r, 1])] if found[r] else None for r in range(12)] == want["w700_first12"]
+
+
+def test_rollmean_threshold_arithmetic_is_pandas():
+    """bot = t.mean() - 0.5 * t.std() of t = rolling(w).mean(): the oracle's Kahan add/remove + nanops restatement against
+    real pandas (when installed), bit for bit, including windows longer than the read and constant reads."""
+    pd = pytest.importorskip("pandas")
+    import warnings
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        n = int(rng.integers(1, 12000)); w = int(rng.choice([1, 2, 7, 100, 2000, 2000, 5000]))
+        sig = rng.integers(1, 1200, n)
+        if trial % 7 == 0:
+            sig[:] = sig[0]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = pd.Series(sig).rolling(window=w).mean()
+            mn, sd = t.mean(), t.std()
+            bot = mn - sd * 0.5
+        _, thr = oracle.rollmean_seg(sig, oracle.RollmeanCfg(w=w), want_thresholds=True)
+        for a, b in ((thr[0], bot), (thr[1], mn), (thr[2], sd)):
+            assert a == b or (np.isnan(a) and np.isnan(b)), (trial, n, w, thr, bot, mn, sd)

@@ -179,3 +179,10 @@ def test_adversarial_shapes_never_violate_the_bound(harness):
         assert diag[4] == 0, (trial, n, m, kind)
         proven += int(diag[2] == 0)
     assert proven >= 50
+
+
+def test_branch_free_split_rule_equals_the_loops(harness):
+    """sqk_tree_depth7 / sqk_tree_leaf7 (sqk_stats3.cuh's form of numpy's split rule) == the loops, every n <= 8192."""
+    harness.stats_tree_check7.argtypes = [C.c_int]
+    harness.stats_tree_check7.restype = C.c_int
+    assert sum(harness.stats_tree_check7(n) for n in range(1, 8193)) == 0
