@@ -312,7 +312,7 @@ def segmenter_block(ctx, dev, peak, steps):
             if refload.available():
                 try:
                     import types
-                    ref = refload.load_segmenter()
+                    ref = refload.load("segmenter")
                     a = types.SimpleNamespace(error=5, corrector=50, window=150, seg_dist=50, std_scale=0.75, stall_len=0.25,
                                               lim_hi=900, lim_low=0)
                     t0 = time.perf_counter()
@@ -344,17 +344,82 @@ def segmenter_block(ctx, dev, peak, steps):
     return out
 
 
-def cli_block():
-    """Wall-clock reads/s of the two drop-in command lines on a generated SquigglePull-style TSV (page cache warm),
-    stdout to /dev/null, next to the CPU path on the first lines of the same file."""
+def cli_block(dev, motif):
+    """Wall-clock reads/s of the two drop-in command lines (fresh process each: interpreter start, CUDA context, text
+    parsing, GPU path, row formatting) on a generated SquigglePull-style TSV of the benchmark's read shape (page cache
+    warm), next to the reference's per-line path on the first lines of the same file."""
+    import contextlib
+    import io
+    import types
+
+    import oracle
+    from oracle import refload
+    from squigglekit_b200 import cli_bench
+    n = int(os.environ.get("SQK_CLI_BENCH_READS", "100000"))
+    out = {"reads": n, "n_samples": 4096, "file": "fast5, readID, 6 spare columns, 4096 int16 samples per line (SquigglePull.py:243-253 layout)"}
+    sig_path, model_path, gen_s = cli_bench.generate(n, 4096, motif, device=dev)
     try:
-        from squigglekit_b200 import cli_bench
-    except Exception as e:                                      # pragma: no cover
-        return {"unavailable": f"{type(e).__name__}: {e}"}
-    try:
-        return cli_bench.run()
-    except Exception as e:
-        return {"unavailable": f"{type(e).__name__}: {e}"}
+        out["file_bytes"] = os.path.getsize(sig_path)
+        out["generate_seconds"] = gen_s
+        out["motifseq"] = cli_bench.time_cli("MotifSeq.py", ["-s", sig_path, "-m", model_path, "--scale", "zscale"], n)
+        out["segmenter"] = cli_bench.time_cli("segmenter.py", ["-s", sig_path, "--start_col", "8", "-k", "-u"], n)
+        # ---- the reference's per-line path on the first lines of the same file, one core ------------------------------
+        n_ref = 200
+        with open(sig_path, "rt") as fh:
+            lines = [next(fh) for _ in range(n_ref)]
+        import scipy.stats as st
+        L = max(1, motif.size // 8)
+        t0 = time.perf_counter()
+        sink = io.StringIO()
+        for line in lines:                       # MotifSeq.py:267-298 + get_region_multi :431-449, mlpy -> the oracle's C port
+            l = line.strip("\n").split("\t")
+            sig = np.array([float(i) for i in l[8:]], dtype=float)
+            sig = sig[(sig > 0) & (sig < 1200)]
+            sig = (sig - sig.mean()) / sig.std()
+            dist, cost, path = oracle.dtw_subsequence(motif, sig)            # MotifSeq.py:437-439
+            start, end = path[1][0], path[1][-1]
+            mod_mean = (2.90 * L) + -9.6
+            mod_stdev = mod_mean * 0.08468
+            Z = (dist - mod_mean) / mod_stdev
+            p_value = st.norm.cdf(Z)
+            sink.write("{}\t{}\t{}\t{}\t{}\t{}\t{}\t{}\t{}\t{}\t{}\t{}\n".format(l[0], l[1], "m", start, end, end - start, dist, mod_mean, mod_stdev, Z, p_value, (1 - p_value) * 100))
+        dt = time.perf_counter() - t0
+        out["motifseq_reference"] = {"value": n_ref / dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                                     "sample": f"first {n_ref} lines: the reference's per-line Python (float() per field, outlier cut, z-score, row formatting) with mlpy.dtw_subsequence replaced by the oracle's C port (full matrix + back-trace), {dt:.1f} s"}
+        kind = "port"
+        if refload.available():
+            try:
+                ref = refload.load("segmenter")
+                a = types.SimpleNamespace(error=5, corrector=50, window=150, seg_dist=50, std_scale=0.75, stall_len=0.25,
+                                          lim_hi=900, lim_low=0, stall=True, stall_start=300, gap=False, gap_dist=3000)
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+                    for line in lines:           # segmenter.py:194-230
+                        l = line.strip("\n").split("\t")
+                        sig = np.array([int(i) for i in l[8:]], dtype=int)
+                        sig = ref.scale_outliers(sig[:-1], a)
+                        ref.get_segs(sig, a)
+                dt = time.perf_counter() - t0
+                kind = "reference"
+                out["segmenter_reference"] = {"value": n_ref / dt, "unit": "reads/s", "cores": 1, "kind": "reference",
+                                              "sample": f"first {n_ref} lines through the reference's own parsing, scale_outliers and get_segs (pure Python), {dt:.1f} s"}
+            except Exception:
+                kind = "port"
+        if kind == "port":
+            t0 = time.perf_counter()
+            for line in lines:
+                l = line.strip("\n").split("\t")
+                sig = np.array([int(i) for i in l[8:]], dtype=int)[:-1]
+                sig = sig[(sig > 0) & (sig < 900)]
+                oracle.get_segs(sig)
+            dt = time.perf_counter() - t0
+            out["segmenter_reference"] = {"value": n_ref / dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                                          "sample": f"first {n_ref} lines: the reference's per-line Python parsing with get_segs replaced by its C restatement, {dt:.1f} s (the pure-Python get_segs runs ~640 reads/s, SURVEY §6)"}
+        out["motifseq"]["vs_reference"] = out["motifseq"]["value"] / out["motifseq_reference"]["value"]
+        out["segmenter"]["vs_reference"] = out["segmenter"]["value"] / out["segmenter_reference"]["value"]
+    finally:
+        cli_bench.cleanup(sig_path)
+    return out
 
 
 def main():
@@ -662,7 +727,10 @@ def main():
                 line["segmenter"] = segmenter_block(ctx, dev, peak, steps=5)
             except Exception as e:
                 line["segmenter"] = {"unavailable": f"{type(e).__name__}: {e}"}
-            line["cli_e2e"] = cli_block()
+            try:
+                line["cli_e2e"] = cli_block(dev, motif)
+            except Exception as e:
+                line["cli_e2e"] = {"unavailable": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if h_sig is not None:
         sqk.pinned_free(h_sig)

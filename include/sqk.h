@@ -226,6 +226,36 @@ SQK_API int sqk_segmenter_f64(sqk_ctx *ctx, const double *signals, const int64_t
                               const sqk_seg_params *params, int mem, int32_t *segs, int32_t *n_segs);
 
 /* ---------------------------------------------------------------------------------------
+ * SquigglePull signal text (host side, no GPU work): the `-s` input of both command lines.
+ *   fast5 <TAB> readID [<TAB> digitisation <TAB> offset <TAB> range <TAB> sampling_rate] <TAB> s0 <TAB> s1 ...
+ * written by SquigglePull.py:243-253 (print_data), read by MotifSeq.py:252-298 (signal from column 8) and
+ * segmenter.py:179-230 (signal from column 4) one float() / int() per field.
+ *
+ * sqk_tsv_parse cuts `text` into lines and parses the signal fields of every line (from column start_col on) into the
+ * int16 batch layout of sqk_motifseq / sqk_segmenter, in parallel over the lines.  Per line i: line_begin[i] (byte offset
+ * of the line), sig_begin[i] (byte offset of the first signal field: the head columns are text[line_begin[i] ..
+ * sig_begin[i] - 1)), offsets[i .. i+1] (its samples), status[i] (flags below; a flagged line's samples are not valid and
+ * the caller sends the line through its float path).  Stops in front of an incomplete last line (unless is_final), after
+ * max_lines lines, or in front of the line that would overflow max_samples.  *n_lines = lines parsed, *consumed = bytes
+ * used.  n_threads <= 0: all host threads.
+ *
+ * sqk_tsv_format writes "<head> <TAB> s0 <TAB> s1 ... <NL>" per read (heads concatenated, head_offsets[n_reads + 1]).
+ * Returns the bytes written, or minus the bytes needed when cap is too small (out may be NULL to ask).
+ * ------------------------------------------------------------------------------------- */
+#define SQK_TSV_NO_SIGNAL 1   /* fewer than start_col + 1 columns                                  */
+#define SQK_TSV_NOT_INT16 2   /* a field is not a plain integer in [-32768, 32767] (pA output ...) */
+#define SQK_TSV_ALL_ZERO 4    /* every sample is 0: the reference prints "No Signal found"           */
+SQK_API int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int start_col, int64_t max_lines,
+                          int64_t max_samples, int n_threads, int16_t *samples, int64_t *offsets, int64_t *line_begin,
+                          int64_t *sig_begin, int32_t *status, int64_t *n_lines, int64_t *consumed);
+/* first n_cols columns of every parsed line, "c0 <TAB> c1 <NL>" each, gathered into out (bytes written, or minus the bytes
+ * needed when cap is too small / out is NULL) */
+SQK_API int64_t sqk_tsv_heads(const char *text, const int64_t *line_begin, const int64_t *sig_begin, int64_t n_lines,
+                              int n_cols, char *out, int64_t cap);
+SQK_API int64_t sqk_tsv_format(const int16_t *samples, const int64_t *offsets, int64_t n_reads, const char *heads,
+                               const int64_t *head_offsets, int n_threads, char *out, int64_t cap);
+
+/* ---------------------------------------------------------------------------------------
  * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the
  * launching stream around each launch.  Off by default.  Reading the counters synchronises.
  * ------------------------------------------------------------------------------------- */

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqk.so")
 
 SQK_MEM_HOST, SQK_MEM_DEVICE = 0, 1
+SQK_ERR_ARG, SQK_ERR_CUDA, SQK_ERR_NOMEM, SQK_ERR_UNSUPPORTED = -1, -2, -3, -4
 SCALE = {"zscale": 0, "medmad": 1, "none": 2}
 PRECISION = {"fp64": 0, "fp32": 1}
 K_STATS, K_DTW, K_SEG_FSM, K_DTW_LB, K_DTW_WIN, K_COUNT = 0, 1, 2, 3, 4, 5
@@ -61,7 +62,7 @@ EXPORTS = [
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
     "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
     "sqk_ctx_get_launches", "sqk_ctx_set_stats_generation", "sqk_device_alloc", "sqk_device_free", "sqk_ipc_export", "sqk_ipc_open",
-    "sqk_ipc_close", "sqk_rollmean", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
+    "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
 ]
 
 _lib = None
@@ -78,6 +79,7 @@ def lib() -> C.CDLL:
             "(or `python -c 'import __graft_entry__ as g; g.build()'`). squigglekit_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.sqk_tsv_format.restype = i64
     L.sqk_version.restype = C.c_int
     L.sqk_last_error.restype = C.c_char_p
     L.sqk_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
@@ -114,8 +116,12 @@ def lib() -> C.CDLL:
     L.sqk_ctx_set_flag_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int]
     L.sqk_peer_signal.argtypes = [vp, C.c_uint64]
     L.sqk_peer_wait.argtypes = [vp, C.c_uint64]
+    L.sqk_tsv_parse.argtypes = [vp, i64, C.c_int, C.c_int, i64, i64, C.c_int, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.sqk_tsv_format.argtypes = [vp, vp, i64, vp, vp, C.c_int, vp, i64]
+    L.sqk_tsv_heads.argtypes = [vp, vp, vp, i64, C.c_int, vp, i64]
+    L.sqk_tsv_heads.restype = i64
     for name in EXPORTS:
-        if name not in ("sqk_version", "sqk_last_error"):
+        if name not in ("sqk_version", "sqk_last_error", "sqk_tsv_format", "sqk_tsv_heads"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

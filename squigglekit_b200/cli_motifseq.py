@@ -83,6 +83,33 @@ def format_row(fast5, read_id, name, start, end, dist, m, b, std, L, extract=Non
     return "\t".join("{}".format(c) for c in cols)
 
 
+def format_rows(heads, names, hits, m, b, std, L):
+    """The same rows for a whole batch: the per-model constants once, Z / p-value / probability as arrays (the same
+    IEEE operations and the same scipy ndtr as the scalar expressions), one join per row.  heads: [(fast5, readID)];
+    hits: structured [n_reads, n_models].  Reads with a status hit (start < 0) are skipped: -> (rows, skipped indices)."""
+    import scipy.stats as st
+    rows, skipped = [], []
+    n = len(heads)
+    cols = []
+    for c, name in enumerate(names):
+        mod_mean = (m * L[c]) + b
+        mod_stdev = mod_mean * std
+        dist = hits["dist"][:, c].astype(np.float64)
+        Z = (dist - mod_mean) / mod_stdev
+        p_value = st.norm.cdf(Z)
+        hit_P = (1 - p_value) * 100
+        cols.append((name, hits["start"][:, c].tolist(), hits["end"][:, c].tolist(), dist.tolist(), "{}".format(mod_mean),
+                     "{}".format(mod_stdev), Z.tolist(), p_value.tolist(), hit_P.tolist()))
+    for r in range(n):
+        f5, rid = heads[r]
+        for name, start, end, dist, mm, ms, Z, pv, hp in cols:
+            if start[r] < 0:
+                skipped.append((r, start[r]))
+                continue
+            rows.append(f"{f5}\t{rid}\t{name}\t{start[r]}\t{end[r]}\t{end[r] - start[r]}\t{dist[r]}\t{mm}\t{ms}\t{Z[r]}\t{pv[r]}\t{hp[r]}")
+    return rows, skipped
+
+
 def _opener(path):
     return gzip.open if path.endswith('.gz') else open
 
@@ -189,6 +216,50 @@ def flush(ctx, args, batch, model, m_order, L, out):
     batch.clear()
 
 
+def run_signal_file(ctx, args, model, m_order, L, out):
+    """-s input through the batched text reader (squigglekit_b200.tsv): a batch of plain int16 lines goes from the parsed
+    pinned buffer straight into one libsqk call and comes back as vectorised rows; a batch with anything else in it
+    (pA values, empty lines, all-zero reads) or -x takes the per-line path with the reference's messages."""
+    from . import tsv
+    models = [model[n] for n in m_order]
+    with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
+        for b in rd:
+            if not b.status.any() and not args.sig_extract:
+                heads = []
+                for i in range(b.n):
+                    h = b.head(i)
+                    heads.append((h[0], h[1] if len(h) > 1 else ""))
+                hits, _ = ctx.motifseq(b.signals[:int(b.offsets[b.n])], b.offsets, models, scale=args.scale,
+                                       scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision, want_kept=False)
+                rows, skipped = format_rows(heads, m_order, hits, args.slope, args.intercept, args.std_const, L)
+                for r, code in skipped:
+                    why = "no samples left after outlier removal" if code == -1 else "MAD is 0: med-MAD scaling undefined"
+                    sys.stderr.write("{} {}: {} - skipped\n".format(heads[r][0], heads[r][1], why))
+                if rows:
+                    out.write("\n".join(rows) + "\n")
+                continue
+            batch = []
+            for i in range(b.n):
+                h = b.head(i)
+                if b.status[i] & tsv.NO_SIGNAL:
+                    sys.stderr.write("No Signal found - please check signal format\n")
+                    continue
+                if b.status[i] == 0:
+                    batch.append((h[0], h[1] if len(h) > 1 else "", b.sig(i).copy()))
+                    continue
+                vals = np.fromstring(b.tail_text(i), dtype=np.float64, sep='\t')
+                if not vals.any():
+                    sys.stderr.write("No Signal found - please check signal format\n")
+                    continue
+                ints = np.rint(vals)
+                if np.array_equal(ints, vals) and ints.min() >= -32768 and ints.max() <= 32767:
+                    sig = ints.astype(np.int16)
+                else:
+                    sig = vals
+                batch.append((h[0], h[1] if len(h) > 1 else "", sig))
+            flush(ctx, args, batch, model, m_order, L, out)
+
+
 def main(argv=None):
     parser = build_parser()
     raw_args = sys.argv[1:] if argv is None else list(argv)
@@ -240,7 +311,9 @@ def main(argv=None):
 
     with Context(args.device) as ctx:
         batch, n_samples = [], 0
-        for rec in iter_reads(args):
+        if args.signal:
+            run_signal_file(ctx, args, model, m_order, L, out)
+        for rec in ([] if args.signal else iter_reads(args)):
             batch.append(rec)
             n_samples += rec[2].size
             if n_samples >= BATCH_SAMPLES or len(batch) >= BATCH_READS:

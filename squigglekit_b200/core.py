@@ -434,16 +434,15 @@ def hits_from_torch(hits_u8) -> np.ndarray:
 
 def segs_to_lists(segs: np.ndarray, n_segs: np.ndarray):
     """Batch output -> what get_segs returns per read: list of [start, end] or False."""
-    out = []
     cap = segs.shape[1]
-    for r in range(n_segs.shape[0]):
-        n = int(n_segs[r])
+    nl = n_segs.tolist()
+    for r, n in enumerate(nl):
         if n < 0:
             raise ValueError(f"read {r} is longer than the max_read_len passed to segmenter()")
         if n > cap:
             raise OverflowError(f"read {r}: {n} segments > max_segs={cap}")
-        out.append([[int(segs[r, i, 0]), int(segs[r, i, 1])] for i in range(n)] if n else False)
-    return out
+    sl = segs.tolist()
+    return [sl[r][:n] if n else False for r, n in enumerate(nl)]
 
 
 def test_segs(segs, cfg: SegConfig):

@@ -656,6 +656,22 @@ static sqk_lb_launcher pick_lb(int L)
     }
 }
 
+// float64 launcher with the most lanes per read that the motif length allows (at least 2 rows per lane)
+static void pick_dtw_wide(int N, int *L_io, int *K_io, sqk_dtw_launcher *fn_io)
+{
+    static const int kmin[3] = {SQK_DTW_L8_KMIN, SQK_DTW_L16_KMIN, SQK_DTW_L32_KMIN};
+    static const int kmax[3] = {SQK_DTW_L8_KMAX, SQK_DTW_L16_KMAX, SQK_DTW_L32_KMAX};
+    static const int lanes[3] = {8, 16, 32};
+    static const sqk_dtw_launcher f64[3] = {sqk_launch_dtw_f64_l8, sqk_launch_dtw_f64_l16, sqk_launch_dtw_f64_l32};
+    for (int li = 2; li >= 0; li--) {
+        const int L = lanes[li], K = (N + L - 1) / L;
+        if (L <= *L_io) return;                       // not wider than the default
+        if (K < kmin[li] || K > kmax[li] || K < 2) continue;
+        *L_io = L; *K_io = K; *fn_io = f64[li];
+        return;
+    }
+}
+
 // Exact (float64) requests run as the two-pass plan when the reads are long enough for windows to pay:
 // the float32 lower-bound scan + float64 windows (sqk_dtw_plan.cuh).  Same results bit for bit.
 static bool want_two_pass(const sqk_ctx *c, const sqk_motif_params *p, int N, int64_t max_len)
@@ -674,7 +690,7 @@ static int check_motif_params(const sqk_motif_params *p)
     return SQK_OK;
 }
 
-#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head, [5] #long window jobs
+#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head
 
 // stats + the DTW of every model over a device-resident View; d_hits is [n_reads][n_models]
 static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
@@ -736,13 +752,12 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         b.hits = a.hits; b.hit_stride = a.hit_stride;
         b.counter = ctr;
         b.jobs = (DtwJob *)s.jobs.p; b.n_jobs = ctr + 1;
-        b.n_long = ctr + 5; b.jobs_cap = (int)(v.n_reads * SQK_LB_MAX_CLUSTERS);
         b.reads = (LbRead *)s.lbreads.p;
         b.xmax_abs = xmax;
         b.W = sqk_lb_window(N);
         if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the fallback
         b.short_len = 2 * (b.W + N);
-        b.long_cols = 4 * (b.W + N);             // a typical window job is W + 1 + a few columns
+        { static int env_cols = -1; if (env_cols < 0) { const char *ec = getenv("SQK_LB_COLS"); env_cols = ec ? atoi(ec) : 0; } b.cols = (env_cols == 2 || env_cols == 4) ? env_cols : 0; }   // experiments
         TRY(tick(c, SQK_K_DTW_LB, st, &eb));
         cudaError_t e = pick_lb(LL)(LK, b, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW lower-bound launch (N=%d, K=%d, L=%d): %s", N, LK, LL, cudaGetErrorString(e));
@@ -750,7 +765,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
 
         TRY(tick(c, SQK_K_DTW_WIN, st, &eb));
         a.counter = ctr + 2;
-        a.jobs = b.jobs; a.n_jobs = ctr + 1; a.n_long = ctr + 5; a.jobs_cap = b.jobs_cap;
+        a.jobs = b.jobs; a.n_jobs = ctr + 1;
         a.job_out = (sqk_hit *)s.jobres.p; a.job_out_stride = 1;
         e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW window launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
@@ -763,10 +778,17 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         sqk_dtw_finalize_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(f);
         CU(cudaGetLastError());
         a.counter = ctr + 4;
-        a.jobs = f.fb_jobs; a.n_jobs = ctr + 3; a.n_long = nullptr; a.jobs_cap = 0;
+        a.jobs = f.fb_jobs; a.n_jobs = ctr + 3;
         a.job_out = a.hits; a.job_out_stride = a.hit_stride;
-        e = fn(K, a, c->n_sms, st);
-        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        // The (few) full-length jobs run at the latency of one read: give each as many lanes as the motif allows, so that a
+        // lane has few rows per column step (N = 80: 3 rows on 32 lanes instead of 10 on 8 -- same bits, a third of the time).
+        {
+            int FL = L, FK = K;
+            sqk_dtw_launcher ffn = fn;
+            if (!c->force_lanes) pick_dtw_wide(N, &FL, &FK, &ffn);
+            e = ffn(FK, a, c->n_sms, st);
+            if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, FK, FL, cudaGetErrorString(e));
+        }
         c->n_launches += 4;                      // lower-bound scan, windows, finalize, fallback
         if (po.n) {                              // the (few) reads the fallback just wrote
             sqk_publish_kernel<<<8, 256, 0, st>>>(a.hits, a.hit_stride, f.fb_jobs, ctr + 3, (int)v.n_reads, po);
@@ -1225,7 +1247,7 @@ int sqk_ctx_get_plan_counters(sqk_ctx *c, int64_t out[2])
     CU(cudaStreamSynchronize(c->slot[0].stream));
     unsigned h[SQK_CTRS_PER_MODEL];
     CU(cudaMemcpy(h, c->slot[0].counter.p, sizeof(h), cudaMemcpyDeviceToHost));
-    out[0] = (int64_t)h[1] + h[5]; out[1] = h[3];
+    out[0] = h[1]; out[1] = h[3];
     return SQK_OK;
 }
 

@@ -59,8 +59,6 @@ struct DtwArgs {
     // JOBS variant only
     const DtwJob *jobs;       // work items
     const unsigned int *n_jobs;   // how many (device memory: produced by the previous kernel)
-    const unsigned int *n_long;   // or null: that many more jobs sit at the END of the list (jobs[jobs_cap-1-i]) and go first
-    int jobs_cap;
     sqk_hit *job_out;         // job_out[job.out * job_out_stride]
     int job_out_stride;
 };
@@ -143,8 +141,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
 
     int64_t alloc_lo = a.alloc_lo, alloc_hi = a.alloc_hi;
     resolve_bounds(a.offsets, a.read0, a.n_reads, alloc_lo, alloc_hi);
-    const unsigned n_long = (JOBS && a.n_long) ? *a.n_long : 0u;
-    const unsigned n_items = JOBS ? *a.n_jobs + n_long : (unsigned)a.n_reads;
+    const unsigned n_items = JOBS ? *a.n_jobs : (unsigned)a.n_reads;
 
     const int lane = threadIdx.x & 31;
     const int l = lane % L;            // lane within the group
@@ -190,7 +187,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
                 if (idx >= n_items) {
                     exhausted = true;
                 } else if constexpr (JOBS) {
-                    const DtwJob jb = idx < n_long ? a.jobs[a.jobs_cap - 1 - (int)idx] : a.jobs[idx - n_long];
+                    const DtwJob jb = a.jobs[idx];
                     my_read = jb.out;
                     const int64_t r = a.read0 + jb.read;
                     begin = a.offsets[r];

@@ -38,12 +38,11 @@ struct LbArgs {
     unsigned int *counter;    // work queue head, zeroed before launch
     DtwJob *jobs;             // job list (capacity n_reads * SQK_LB_MAX_CLUSTERS)
     unsigned int *n_jobs;     // its length, zeroed before launch
-    unsigned int *n_long;     // jobs of more than long_cols columns are stored from the END of the list (jobs[jobs_cap-1-i]) ...
-    int jobs_cap, long_cols;  // ... and taken FIRST by the exact kernel: a long job started last would set the launch time alone
     LbRead *reads;            // [n_reads]
     double xmax_abs;          // max |motif point|
     int W;                    // window columns in front of a cluster
     int short_len;            // reads with n_kept <= short_len skip pass 1 (one full-length job)
+    int cols;                 // signal columns per wavefront step: 2, 4, or 0 = the launcher's rule
 };
 
 // Shared-memory ring access by 32-bit shared address.  Every group's ring is aligned to its size (RC*4 bytes), so
@@ -66,6 +65,7 @@ struct LbWatch {
     float thr_u;           // thr + an upper bound of (j + N) * w over the current block of steps: the cheap test on U
                            // (-inf in every other lane)
     float aeps, bslack, w;
+    float wstep;           // COLS * w, rounded down: what the free-start row advances by per wavefront step
     int n;                 // columns of the read
     int N;
 };
@@ -137,9 +137,10 @@ __device__ __forceinline__ void lb_step2(const float (&ci)[K], float (&co)[K], c
 {
     float up_a = __shfl_up_sync(SQK_FULL_MASK, bot_a, 1, L);
     float up_b = __shfl_up_sync(SQK_FULL_MASK, bot_b, 1, L);
-    const float virt_b = sqk_lb_virtual_next(tf, wt.w); // free-start row: j*w in column j (lane 0 is at columns t, t+1)
-    if (l == 0) { up_a = tf; up_b = virt_b; }
-    tf = sqk_lb_virtual_next(virt_b, wt.w);
+    // free-start row: a lower bound of j*w in column j (lane 0 is at columns t, t+1); both columns of the step take the
+    // value of the first one (smaller is still a lower bound; it costs one w of tightness), one rounded-down add per step
+    if (l == 0) { up_a = tf; up_b = tf; }
+    tf = sqk_add_rd(tf, wt.wstep);
     const float2 y = lb_lds2(raddr);
     raddr = lb_ring_next2<16 * L * 4>(raddr);
     float dg_a = prev_up_b;                              // row above, column j-1
@@ -156,25 +157,68 @@ __device__ __forceinline__ void lb_step2(const float (&ci)[K], float (&co)[K], c
         ua = a; ub = b;
         co[k] = b;
     }
-    bot_a = ua; bot_b = ub;
-    if (fminf(ua, ub) <= wt.thr_u) {                     // rare: a column of the last row that may be a candidate
-        const int j = t - 2 * (L - 1);
-        lb_candidate(ua, j, wt, cl, ck, n_ref, cursor0, 8 * L, W);
-        lb_candidate(ub, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, W);
-    }
+    bot_a = ua; bot_b = ub;                              // (the caller tests the last row for candidates: once per two steps)
 }
 
+__device__ __forceinline__ float4 lb_lds4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <int RING_BYTES>
+__device__ __forceinline__ unsigned lb_ring_next4(unsigned addr)
+{
+    return (addr & ~(unsigned)(RING_BYTES - 1)) | ((addr + 16u) & (unsigned)(RING_BYTES - 1));
+}
+
+// Four columns per step: this lane's K rows of columns j = t - 4l .. j + 3.  Cell (k, q) needs (k-1, q), (k-1, q-1) and
+// (k, q-1): four dependency chains one cell apart; the per-step work that does not scale with the cells (shuffles per
+// column aside: ring load and address, free-start row, loop control, the candidate test) is paid once per 4K cells.
 template <int K, int L, bool RAGGED>
+__device__ __forceinline__ void lb_step4(const float (&ci)[K], float (&co)[K], const float (&x)[K], unsigned &raddr, int l,
+                                         bool pass0, float &tf, float (&bot)[4], float &prev_up_d, const LbWatch &wt)
+{
+    float u0 = __shfl_up_sync(SQK_FULL_MASK, bot[0], 1, L);
+    float u1 = __shfl_up_sync(SQK_FULL_MASK, bot[1], 1, L);
+    float u2 = __shfl_up_sync(SQK_FULL_MASK, bot[2], 1, L);
+    float u3 = __shfl_up_sync(SQK_FULL_MASK, bot[3], 1, L);
+    if (l == 0) { u0 = tf; u1 = tf; u2 = tf; u3 = tf; }  // free-start row: a lower bound of j*w for the step's first column
+    tf = sqk_add_rd(tf, wt.wstep);
+    const float4 y = lb_lds4(raddr);
+    raddr = lb_ring_next4<32 * L * 4>(raddr);
+    const float up0 = u0, up1 = u1, up2 = u2, up3 = u3;
+    float dg = prev_up_d;                                // row above, column j-1
+    prev_up_d = u3;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float lf = ci[k];                          // this row, column j-1
+        float a = sqk_lb_cell(x[k], y.x, fminf(fminf(u0, dg), lf));
+        if (RAGGED && k == 0 && pass0) a = up0;          // pass-through slot (only when L*K != N)
+        float b = sqk_lb_cell(x[k], y.y, fminf(fminf(u1, u0), a));
+        if (RAGGED && k == 0 && pass0) b = up1;
+        float c = sqk_lb_cell(x[k], y.z, fminf(fminf(u2, u1), b));
+        if (RAGGED && k == 0 && pass0) c = up2;
+        float d = sqk_lb_cell(x[k], y.w, fminf(fminf(u3, u2), c));
+        if (RAGGED && k == 0 && pass0) d = up3;
+        dg = lf;
+        u0 = a; u1 = b; u2 = c; u3 = d;
+        co[k] = d;
+    }
+    bot[0] = u0; bot[1] = u1; bot[2] = u2; bot[3] = u3;
+}
+
+template <int K, int L, bool RAGGED, int COLS>
 __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_kernel(const LbArgs a)
 {
     constexpr int G = 32 / L;          // reads per warp
-    constexpr int RC = 16 * L;         // ring capacity (entries), power of two
-    constexpr int COLS = SQK_LB_COLS;
+    constexpr int RC = (COLS == 4 ? 32 : 16) * L;         // ring capacity (entries), power of two
     constexpr int LAG = COLS * (L - 1);      // columns the last lane runs behind lane 0
     // columns between ring refills: S + CH + LAG <= RC so that no entry is overwritten before its last reader
-    constexpr int S = (L == 1) ? 8 : (COLS == 2 ? 6 * L : 7 * L);
+    constexpr int S = (L == 1) ? 8 : (COLS == 4 ? 12 * L : (COLS == 2 ? 6 * L : 7 * L));
     constexpr int CH = 8 * L;          // raw samples fetched per refill
     static_assert(S % (2 * COLS) == 0 && S + CH + LAG <= RC, "ring schedule");
+    static_assert(2 * CH >= S + LAG, "lb_candidate refreshes the cheap threshold for 2 * CH columns ahead: must cover the block");
 
     // Each group's ring must be aligned to its size (RC*4 bytes) in the shared address space for lb_ring_next; static
     // shared memory starts behind a reserved kilobyte, so the alignment is established here, not by __align__.
@@ -210,10 +254,15 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
         x[k] = (row >= 0 && row < a.N) ? (float)a.model[row] : 0.0f;
     }
 
+    // outlier window lo < v < hi as one unsigned compare (samples are int16; lo / hi are clamped to +-40000 by the host)
+    const int win_lo = a.lo + 1;
+    const bool win_ok = a.hi - 1 >= win_lo;
+    const unsigned win_span = (unsigned)(a.hi - 1 - win_lo);
     const float inf = __int_as_float(0x7f800000);
     float c[K], c2[K];
     float bot = inf, bot_b = inf, prev_up = inf, tf = 0.0f;   // COLS == 2: bot is column A's bottom, prev_up is column B's
-    LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.aeps = 0.0f; wt.bslack = 0.0f; wt.w = 0.0f; wt.n = 0; wt.N = a.N;
+    float bot4[4] = {inf, inf, inf, inf};                      // COLS == 4
+    LbWatch wt; wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.aeps = 0.0f; wt.bslack = 0.0f; wt.w = 0.0f; wt.wstep = 0.0f; wt.n = 0; wt.N = a.N;
     // groups of one warp start in phase and, with equal-length reads, stay in phase: rotate each group's ring by the
     // span its lanes read in one step so that simultaneous reads of different groups fall into different banks
     const int rot = (g * L * COLS) & (RC - 1);
@@ -264,8 +313,7 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         if (l == L - 1) {
                             DtwJob jb; jb.cursor = cursor0; jb.read = (int)idx; jb.col0 = 0; jb.n_cols = n; jb.arg_lo = 0;
                             jb.tainted = 0; jb.out = (int)idx * SQK_LB_MAX_CLUSTERS;
-                            if (n > a.long_cols) a.jobs[a.jobs_cap - 1 - (int)atomicAdd(a.n_long, 1u)] = jb;
-                            else a.jobs[atomicAdd(a.n_jobs, 1u)] = jb;
+                            a.jobs[atomicAdd(a.n_jobs, 1u)] = jb;
                             LbRead rec; rec.min_l = 0.0f; rec.thr = inf; rec.n_jobs = 1; rec.flags = 0;
                             a.reads[idx] = rec;
                         }
@@ -277,10 +325,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
 #pragma unroll
                         for (int k = 0; k < K; k++) c[k] = inf;
                         bot = inf; bot_b = inf;
+                        bot4[0] = inf; bot4[1] = inf; bot4[2] = inf; bot4[3] = inf;
                         prev_up = (l == 0) ? 0.0f : inf;
                         wt.runmin = inf; wt.thr = SQK_LB_THR_INIT; wt.thr_u = -inf; wt.n = n;
                         inv_scale = sqk_lb_inv_scale(scale);
                         wt.w = sqk_lb_width(a.xmax_abs, sqk_lb_ymax(a.lo, a.hi, center, scale));
+                        wt.wstep = sqk_mul_rd((float)COLS, wt.w);
                         sqk_lb_slack(a.N, wt.w, &wt.aeps, &wt.bslack);
                         if (l == L - 1) lbc_reset(*cl);
                     }
@@ -298,12 +348,13 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
             const int64_t blk = cursor + l * 8;
             if (want && blk < end) {
                 smp = load_block8(a.base, blk, alloc_lo, alloc_hi);
+                // samples of the block that belong to the read (blk >= begin - 7), then the outlier window on those
+                const int e_lo = begin > blk ? (int)(begin - blk) : 0;
+                const int e_hi = end - blk < 8 ? (int)(end - blk) : 8;
+                const unsigned inside = ((1u << e_hi) - 1u) & ~((1u << e_lo) - 1u);
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int v = smp.get(e);
-                    const int64_t idx = blk + e;
-                    if (idx >= begin && idx < end && v > a.lo && v < a.hi) keep |= 1u << e;
-                }
+                for (int e = 0; e < 8; e++) keep |= ((unsigned)(smp.get(e) - win_lo) <= win_span) ? 1u << e : 0u;
+                keep &= win_ok ? inside : 0u;
             }
             const int cnt = __popc(keep);
             int incl = cnt;
@@ -315,11 +366,19 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
             const int group_total = __shfl_sync(SQK_FULL_MASK, incl, L - 1, L);
             if (keep) {
                 int pos = wcount + incl - cnt;
+                const int p0 = (pos + rot) & (RC - 1);
+                if (keep == 0xffu && p0 <= RC - 8) {
+                    // the common block: all eight samples kept, no wrap inside it -- eight stores at fixed offsets
+                    float *dst = ring + p0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    if (keep & (1u << e)) {
-                        ring[(pos + rot) & (RC - 1)] = sqk_lb_y32((double)smp.get(e), center, inv_scale);
-                        pos++;
+                    for (int e = 0; e < 8; e++) dst[e] = sqk_lb_y32((double)smp.get(e), center, inv_scale);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (keep & (1u << e)) {
+                            ring[(pos + rot) & (RC - 1)] = sqk_lb_y32((double)smp.get(e), center, inv_scale);
+                            pos++;
+                        }
                     }
                 }
             }
@@ -334,13 +393,41 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
         // the cheap candidate test of this block of steps: U <= thr + (largest (j + N) * w of the block)
         if (l == L - 1 && !done) wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(t + S + a.N), wt.w));
         tf = sqk_lb_virtual((float)t, wt.w);          // free-start row at the block's first column; steps add w
-        if constexpr (COLS == 2) {
+        if constexpr (COLS == 4) {
+#pragma unroll 1
+            for (int it = 0; it < S; it += 8) {
+                lb_step4<K, L, RAGGED>(c, c2, x, raddr, l, pass0, tf, bot4, prev_up, wt);
+                const float a1 = bot4[0], b1 = bot4[1], c1 = bot4[2], d1 = bot4[3];
+                lb_step4<K, L, RAGGED>(c2, c, x, raddr, l, pass0, tf, bot4, prev_up, wt);
+                // one test per eight columns of the last row (rare: a column that may be a candidate); in column order
+                if (fminf(fminf(fminf(a1, b1), fminf(c1, d1)), fminf(fminf(bot4[0], bot4[1]), fminf(bot4[2], bot4[3]))) <= wt.thr_u) {
+                    const int j = t - 4 * (L - 1);
+                    lb_candidate(a1, j, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(b1, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(c1, j + 2, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(d1, j + 3, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot4[0], j + 4, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot4[1], j + 5, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot4[2], j + 6, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot4[3], j + 7, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                }
+                t += 8;
+            }
+        } else if constexpr (COLS == 2) {
 #pragma unroll 1
             for (int it = 0; it < S; it += 4) {
                 lb_step2<K, L, RAGGED>(c, c2, x, raddr, l, pass0, t, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
-                t += 2;
-                lb_step2<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
-                t += 2;
+                const float a1 = bot, b1 = bot_b;
+                lb_step2<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t + 2, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
+                // one test per four columns of the last row (rare: a column that may be a candidate); in column order
+                if (fminf(fminf(a1, b1), fminf(bot, bot_b)) <= wt.thr_u) {
+                    const int j = t - 2 * (L - 1);
+                    lb_candidate(a1, j, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(b1, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot, j + 2, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    lb_candidate(bot_b, j + 3, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                }
+                t += 4;
             }
         } else {
 #pragma unroll 1
@@ -362,15 +449,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                     if (cl->tainted[q] < 0) rec.flags |= 4;   // its boundary column had already left the checkpoint ring
                 if (rec.flags == 0) {
                     const int nj = cl->n;
-                    int n_short = 0;
-                    for (int q = 0; q < nj; q++) n_short += (cl->hi[q] - cl->col0[q] + 1 > a.long_cols) ? 0 : 1;
-                    unsigned at = n_short ? atomicAdd(a.n_jobs, (unsigned)n_short) : 0u;
+                    const unsigned at = atomicAdd(a.n_jobs, (unsigned)nj);
                     for (int q = 0; q < nj; q++) {
                         DtwJob jb;
                         jb.cursor = cl->cursor[q]; jb.read = my_read; jb.col0 = cl->col0[q]; jb.n_cols = cl->hi[q] - cl->col0[q] + 1;
                         jb.arg_lo = cl->lo[q] - cl->col0[q]; jb.tainted = cl->tainted[q]; jb.out = my_read * SQK_LB_MAX_CLUSTERS + q;
-                        if (jb.n_cols > a.long_cols) a.jobs[a.jobs_cap - 1 - (int)atomicAdd(a.n_long, 1u)] = jb;   // rare
-                        else a.jobs[at++] = jb;
+                        a.jobs[at + q] = jb;
                     }
                     rec.n_jobs = nj;
                 }

@@ -24,7 +24,7 @@
 #include "sqk_stats2.cuh"
 
 #define SQK_S3_MAXOUT 32            // outliers per read the exception list holds
-#define SQK_S3_PATCH 6              // leaves with an outlier inside that can be patched per read
+#define SQK_S3_PATCH 12             // leaves with an outlier inside that can be patched per read
 #define SQK_S3_SLOTS 128            // leaf slots: depth <= 7 for n <= 8192
 #define SQK_S3_MAX_LEN SQK_S2_MAX_LEN
 #define SQK_S3_MAX_BINS 2048
@@ -306,10 +306,12 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
             else {
                 for (int pi = 0; pi < n_patch; pi++) {
                     const int off = sh.patch_src[pi][0], ln = sh.patch_src[pi][1], c0 = sh.patch_src[pi][2], c1 = sh.patch_src[pi][3];
+                    // the outliers inside this leaf: nearly always one or two
+                    const int adj0 = sh.out_adj[c0], adj1 = c1 - c0 > 1 ? sh.out_adj[c0 + 1] : 0x7fffffff;
                     for (int c = lane; c < ln; c += 32) {
                         const int g = off + c;
-                        int shf = c0;
-                        for (int j = c0; j < c1; j++) shf += (sh.out_adj[j] <= g) ? 1 : 0;   // the outliers inside this leaf
+                        int shf = c0 + ((adj0 <= g) ? 1 : 0) + ((adj1 <= g) ? 1 : 0);
+                        for (int j = c0 + 2; j < c1; j++) shf += (sh.out_adj[j] <= g) ? 1 : 0;
                         s3_sts_u16(patch + 256u * (unsigned)pi + 2u * (unsigned)c, s2_lds_s16(bufs + 2u * (unsigned)(h0 + g + shf)));
                     }
                 }

@@ -1,0 +1,221 @@
+"""SquigglePull signal text, batched: the ``-s`` input of MotifSeq.py / segmenter.py / dRNA_segmenter.py.
+
+    fast5 <TAB> readID [<TAB> digitisation <TAB> offset <TAB> range <TAB> sampling_rate] <TAB> s0 <TAB> s1 ...
+
+is what SquigglePull.py:243-253 prints and what MotifSeq.py:252-298 (signal from column 8) and segmenter.py:179-230
+(signal from column 4) read back with one ``float()`` / ``int()`` per field in a Python list comprehension.  Here the
+file is read in large binary blocks and ``sqk_tsv_parse`` (libsqk, C + OpenMP over the lines) turns every block into
+the int16 batch layout the GPU path consumes -- samples land directly in a pinned buffer, so the following host-mode
+call copies them without staging.  ``write_reads`` is the inverse (``sqk_tsv_format``), i.e. SquigglePull's
+``print_data`` for raw signal.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _cabi
+
+NO_SIGNAL, NOT_INT16, ALL_ZERO = 1, 2, 4
+
+
+@dataclass
+class Batch:
+    """Consecutive lines of the file.  ``signals[offsets[i]:offsets[i+1]]`` are the int16 samples of line i (valid where
+    ``status[i] == 0``); ``head(i)`` its leading columns; ``tail_text(i)`` the raw text of its signal columns;
+    ``heads(k)`` the first k columns of every line (one C call for the batch)."""
+    text: object            # buffer holding the batch's text (memoryview or mmap slice)
+    base: int               # address of text[0]
+    line_begin: np.ndarray
+    sig_begin: np.ndarray
+    offsets: np.ndarray
+    status: np.ndarray
+    signals: np.ndarray
+    n: int
+
+    def head(self, i: int):
+        end = int(self.sig_begin[i])
+        b = bytes(self.text[int(self.line_begin[i]):max(int(self.line_begin[i]), end - 1)])
+        if self.status[i] & NO_SIGNAL:
+            b = bytes(self.text[int(self.line_begin[i]):int(self.line_begin[i + 1])]).rstrip(b"\r\n")
+        return b.decode("utf-8", "replace").split("\t")
+
+    def heads(self, n_cols: int = 2):
+        """-> list of lists: the first ``n_cols`` columns of every line."""
+        lib = _cabi.lib()
+        need = -int(lib.sqk_tsv_heads(self.base, self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.n, n_cols, None, 0))
+        if need <= 0:
+            return []
+        out = bytearray(need)
+        view = (C.c_char * need).from_buffer(out)
+        lib.sqk_tsv_heads(self.base, self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.n, n_cols, C.addressof(view), need)
+        del view
+        return [ln.split("\t") for ln in out.decode("utf-8", "replace").split("\n")[:self.n]]
+
+    def tail_text(self, i: int) -> str:
+        return bytes(self.text[int(self.sig_begin[i]):int(self.line_begin[i + 1])]).rstrip(b"\r\n").decode("utf-8", "replace")
+
+    def sig(self, i: int) -> np.ndarray:
+        return self.signals[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+
+class Reader:
+    """Iterate over a SquigglePull TSV as parsed batches of at most ``max_lines`` lines / ``max_samples`` samples.  A
+    plain file is memory-mapped and parsed in place (no copy of the text is ever made); a .gz file is streamed through a
+    buffer.  The sample buffer is pinned when ``pinned`` (needs the CUDA runtime, i.e. a GPU box)."""
+
+    def __init__(self, path: str, start_col: int, max_lines: int = 16384, max_samples: int = 96 << 20,
+                 block_bytes: int = 128 << 20, pinned: bool = True, n_threads: int = 0):
+        import mmap
+        import os
+        self.lib = _cabi.lib()
+        self.start_col, self.max_lines, self.max_samples = int(start_col), int(max_lines), int(max_samples)
+        self.block_bytes, self.n_threads = int(block_bytes), int(n_threads)
+        self.mm = None
+        self.fh = None
+        if path.endswith(".gz"):
+            self.fh = gzip.open(path, "rb")
+        else:
+            self._file = open(path, "rb")
+            size = os.fstat(self._file.fileno()).st_size
+            if size > 0:
+                self.mm = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ)
+                try:
+                    self.mm.madvise(mmap.MADV_SEQUENTIAL)
+                except Exception:
+                    pass
+                self.mm_arr = np.frombuffer(self.mm, dtype=np.uint8)
+            self.size = size
+        self._pinned = None
+        if pinned:
+            from .core import pinned_empty
+            self._pinned = pinned_empty(self.max_samples, np.int16)
+            self.samples = self._pinned
+        else:
+            self.samples = np.empty(self.max_samples, dtype=np.int16)
+        self.offsets = np.zeros(self.max_lines + 1, dtype=np.int64)
+        self.line_begin = np.zeros(self.max_lines + 1, dtype=np.int64)
+        self.sig_begin = np.zeros(self.max_lines, dtype=np.int64)
+        self.status = np.zeros(self.max_lines, dtype=np.int32)
+        self.buf = bytearray()
+        self.pos = 0
+        self.eof = False
+
+    def close(self):
+        if self.fh is not None:
+            self.fh.close()
+        if self.mm is not None:
+            self.mm_arr = None
+            try:
+                self.mm.close()
+            except BufferError:
+                pass
+            self.mm = None
+        if getattr(self, "_file", None) is not None:
+            self._file.close()
+            self._file = None
+        if self._pinned is not None:
+            from .core import pinned_free
+            pinned_free(self._pinned)
+            self._pinned = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _parse(self, addr, avail, final):
+        n_lines, consumed = C.c_int64(0), C.c_int64(0)
+        rc = self.lib.sqk_tsv_parse(addr, avail, int(final), self.start_col, self.max_lines, self.max_samples,
+                                    self.n_threads, self.samples.ctypes.data, self.offsets.ctypes.data,
+                                    self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.status.ctypes.data,
+                                    C.byref(n_lines), C.byref(consumed))
+        if rc == _cabi.SQK_ERR_NOMEM:
+            raise ValueError("a line of the signal file holds more samples than the batch buffer (%d)" % self.max_samples)
+        if rc != 0:
+            raise RuntimeError("sqk_tsv_parse failed (%d)" % rc)
+        return int(n_lines.value), int(consumed.value)
+
+    def _batch(self, text, base, n):
+        return Batch(text, base, self.line_begin[:n + 1].copy(), self.sig_begin[:n].copy(), self.offsets[:n + 1].copy(),
+                     self.status[:n].copy(), self.samples, n)
+
+    def _fill(self):
+        if self.pos:
+            del self.buf[:self.pos]
+            self.pos = 0
+        chunk = self.fh.read(self.block_bytes)
+        if not chunk:
+            self.eof = True
+        else:
+            self.buf += chunk
+
+    def __iter__(self):
+        if self.fh is None:                                      # memory-mapped plain file
+            if self.mm is None:
+                return
+            pos, base = 0, self.mm_arr.ctypes.data
+            while pos < self.size:
+                n, used = self._parse(base + pos, self.size - pos, True)
+                if n == 0:
+                    return
+                mv = memoryview(self.mm)[pos:pos + used]
+                try:
+                    yield self._batch(mv, base + pos, n)
+                finally:
+                    mv.release()
+                pos += used
+            return
+        while True:                                              # streamed (.gz)
+            if not self.eof and len(self.buf) - self.pos < self.block_bytes // 2:
+                self._fill()
+            avail = len(self.buf) - self.pos
+            if avail == 0:
+                if self.eof:
+                    return
+                continue
+            view = (C.c_char * avail).from_buffer(self.buf, self.pos)
+            try:
+                n, used = self._parse(C.addressof(view), avail, self.eof)
+                if n == 0:
+                    if self.eof:
+                        return
+                else:
+                    mv = memoryview(self.buf)[self.pos:self.pos + used]
+                    try:
+                        yield self._batch(mv, C.addressof(view), n)
+                    finally:
+                        mv.release()
+                    self.pos += used
+            finally:
+                del view
+            if n == 0:
+                self._fill()                                      # the buffered text ends inside a line: bring in more
+
+
+def format_reads(heads, signals: np.ndarray, offsets: np.ndarray, n_threads: int = 0) -> bytes:
+    """``head <TAB> s0 <TAB> s1 ... <NL>`` per read (SquigglePull.py:251-253); heads: list of str, e.g. "f.fast5\\trid"."""
+    lib = _cabi.lib()
+    signals = np.ascontiguousarray(signals, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    enc = [h.encode() if isinstance(h, str) else bytes(h) for h in heads]
+    hoff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in enc], out=hoff[1:])
+    hb = b"".join(enc)
+    need = -int(lib.sqk_tsv_format(signals.ctypes.data, offsets.ctypes.data, n, hb, hoff.ctypes.data, n_threads, None, 0))
+    out = bytearray(need)
+    if need:
+        view = (C.c_char * need).from_buffer(out)
+        got = int(lib.sqk_tsv_format(signals.ctypes.data, offsets.ctypes.data, n, hb, hoff.ctypes.data, n_threads, C.addressof(view), need))
+        del view
+        assert got == need
+    return bytes(out)
+
+
+def write_reads(fh, heads, signals, offsets, n_threads: int = 0):
+    fh.write(format_reads(heads, signals, offsets, n_threads))

@@ -100,3 +100,29 @@ def test_blow5_reader_on_the_reference_example(golden_dir):
     r = recs[0]
     assert r["read_id"] == str(ex["read_id"]) and np.array_equal(r["signal"], ex["raw"])
     assert (r["digitisation"], r["offset"], r["sampling_rate"]) == (8192.0, 16.0, 4000.0)
+
+
+def test_vectorised_rows_equal_the_per_read_rows():
+    """cli_motifseq.format_rows (a batch at a time) prints exactly what format_row prints read by read -- the row
+    get_region_multi prints (MotifSeq.py:441-449), Python float repr and all."""
+    import squigglekit_b200 as sqk
+    from squigglekit_b200 import cli_motifseq
+    rng = np.random.default_rng(8)
+    n, names, L = 500, ["m1", "polyA"], [20, 8]
+    hits = np.zeros((n, 2), dtype=sqk.HIT_DTYPE)
+    hits["start"] = rng.integers(0, 4000, (n, 2)); hits["end"] = hits["start"] + rng.integers(1, 300, (n, 2))
+    hits["dist"] = np.abs(rng.normal(40, 30, (n, 2))) * 10.0 ** rng.integers(-6, 3, (n, 2))
+    hits["dist"][3, 0] = 1e-300; hits["dist"][4, 1] = 1e22; hits["dist"][5, 0] = 48.4
+    hits["start"][7, 1] = hits["end"][7, 1] = -1; hits["start"][9, 0] = hits["end"][9, 0] = -2
+    heads = [(f"f{i}.fast5", f"r{i}") for i in range(n)]
+    rows, skipped = cli_motifseq.format_rows(heads, names, hits, 2.90, -9.6, 0.08468, L)
+    want = []
+    for r in range(n):
+        for c, name in enumerate(names):
+            h = hits[r, c]
+            if int(h["start"]) < 0:
+                continue
+            want.append(cli_motifseq.format_row(heads[r][0], heads[r][1], name, int(h["start"]), int(h["end"]), h["dist"], 2.90, -9.6,
+                                                0.08468, L[c]))
+    assert rows == want
+    assert sorted(skipped) == [(7, -1), (9, -2)]
