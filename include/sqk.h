@@ -58,8 +58,10 @@ enum sqk_mem { SQK_MEM_HOST = 0, SQK_MEM_DEVICE = 1 };
 /* MotifSeq.py:96  --scale {zscale, medmad};  "none" feeds already-centred data through */
 enum sqk_scale { SQK_SCALE_ZSCALE = 0, SQK_SCALE_MEDMAD = 1, SQK_SCALE_NONE = 2 };
 
-/* DTW arithmetic: FP64 reproduces mlpy's float64 recurrence bit for bit (indices and dist);
- * FP32 is the fast mode (dist within 1e-4, indices may differ on near-ties: rate is reported) */
+/* DTW arithmetic.  FP64 reproduces mlpy's float64 recurrence bit for bit (indices and dist).  FP32 asks for "dist within
+ * 1e-4, indices may differ on near-ties" (BASELINE.json north_star); since the exact two-pass plan (float32 lower-bound
+ * scan + float64 windows) is faster than a float32 recurrence with start pointers ever was, FP32 requests are served by
+ * the exact path as well: same results as FP64, which satisfies the looser contract. */
 enum sqk_precision { SQK_PREC_FP64 = 0, SQK_PREC_FP32 = 1 };
 
 typedef struct sqk_ctx sqk_ctx;

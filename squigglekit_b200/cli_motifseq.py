@@ -87,7 +87,7 @@ def format_rows(heads, names, hits, m, b, std, L):
     """The same rows for a whole batch: the per-model constants once, Z / p-value / probability as arrays (the same
     IEEE operations and the same scipy ndtr as the scalar expressions), one join per row.  heads: [(fast5, readID)];
     hits: structured [n_reads, n_models].  Reads with a status hit (start < 0) are skipped: -> (rows, skipped indices)."""
-    import scipy.stats as st
+    from scipy.special import ndtr          # what scipy.stats.norm.cdf evaluates (scipy/stats/_continuous_distns.py: _norm_cdf)
     rows, skipped = [], []
     n = len(heads)
     cols = []
@@ -96,7 +96,7 @@ def format_rows(heads, names, hits, m, b, std, L):
         mod_stdev = mod_mean * std
         dist = hits["dist"][:, c].astype(np.float64)
         Z = (dist - mod_mean) / mod_stdev
-        p_value = st.norm.cdf(Z)
+        p_value = ndtr(Z)
         hit_P = (1 - p_value) * 100
         cols.append((name, hits["start"][:, c].tolist(), hits["end"][:, c].tolist(), dist.tolist(), "{}".format(mod_mean),
                      "{}".format(mod_stdev), Z.tolist(), p_value.tolist(), hit_P.tolist()))
@@ -225,10 +225,7 @@ def run_signal_file(ctx, args, model, m_order, L, out):
     with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
         for b in rd:
             if not b.status.any() and not args.sig_extract:
-                heads = []
-                for i in range(b.n):
-                    h = b.head(i)
-                    heads.append((h[0], h[1] if len(h) > 1 else ""))
+                heads = [(h[0], h[1] if len(h) > 1 else "") for h in b.heads(2)]
                 hits, _ = ctx.motifseq(b.signals[:int(b.offsets[b.n])], b.offsets, models, scale=args.scale,
                                        scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision, want_kept=False)
                 rows, skipped = format_rows(heads, m_order, hits, args.slope, args.intercept, args.std_const, L)

@@ -208,7 +208,7 @@ def run_signal_file(ctx, args, cfg, out):
     with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
         for b in rd:
             if not b.status.any():
-                names = [b.head(i)[0] for i in range(b.n)]
+                names = [h[0] for h in b.heads(1)]
                 segs, nsegs = segment_batch(ctx, b.signals[:int(b.offsets[b.n])], b.offsets, cfg)
                 emit(args, cfg, names, segs, nsegs, out)
                 continue

@@ -102,7 +102,7 @@ struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
-    DevBuf redo, mask, rm_p, rm_masks;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
+    DevBuf redo, mask, rm_p, rm_masks, bnd_a, bnd_b;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -585,8 +585,6 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
     static const int lanes[5] = {1, 4, 8, 16, 32};
     static const sqk_dtw_launcher f64[5] = {sqk_launch_dtw_f64_l1, sqk_launch_dtw_f64_l4, sqk_launch_dtw_f64_l8,
                                             sqk_launch_dtw_f64_l16, sqk_launch_dtw_f64_l32};
-    static const sqk_dtw_launcher f32[5] = {sqk_launch_dtw_f32_l1, sqk_launch_dtw_f32_l4, sqk_launch_dtw_f32_l8,
-                                            sqk_launch_dtw_f32_l16, sqk_launch_dtw_f32_l32};
     auto fits = [&](int li) {
         const int L = lanes[li], K = (N + L - 1) / L;
         if (K < kmin[li] || K > kmax[li]) return false;
@@ -611,7 +609,8 @@ static int pick_dtw(const sqk_ctx *c, int N, int precision, int *L_out, int *K_o
     }
     *L_out = lanes[pick];
     *K_out = (N + lanes[pick] - 1) / lanes[pick];
-    *fn = precision == SQK_PREC_FP32 ? f32[pick] : f64[pick];
+    (void)precision;      // SQK_PREC_FP32 is served by the exact path (see include/sqk.h)
+    *fn = f64[pick];
     return SQK_OK;
 }
 
@@ -676,7 +675,6 @@ static void pick_dtw_wide(int N, int *L_io, int *K_io, sqk_dtw_launcher *fn_io)
 // the float32 lower-bound scan + float64 windows (sqk_dtw_plan.cuh).  Same results bit for bit.
 static bool want_two_pass(const sqk_ctx *c, const sqk_motif_params *p, int N, int64_t max_len)
 {
-    if (p->precision != SQK_PREC_FP64) return false;
     if (c->dtw_plan == SQK_PLAN_SINGLE_PASS) return false;
     if (c->dtw_plan == SQK_PLAN_TWO_PASS) return true;
     return max_len >= 4ll * (sqk_lb_window(N) + N);
@@ -691,6 +689,46 @@ static int check_motif_params(const sqk_motif_params *p)
 }
 
 #define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head
+
+// A motif of more than 1024 points: its rows are cut into nb blocks of <= 1024; block b runs as one launch of the float64
+// kernel's row-block variant over a sub-batch of reads, reading row r0 - 1 of every column from the boundary buffer the
+// previous launch wrote (the free-start row for b = 0) and writing its own last row (the hit for b = nb - 1).  Same
+// recurrence, same tie-breaks: the result is mlpy's bit for bit.  Two boundary buffers of 16 bytes per column per read.
+static int enqueue_long_motif(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_model, int N,
+                              const sqk_motif_params *p, sqk_hit *d_hits, int hit_stride, unsigned *d_counter)
+{
+    const int nb = (N + 32 * SQK_DTW_L32_KMAX - 1) / (32 * SQK_DTW_L32_KMAX);
+    const int rows = (N + nb - 1) / nb;
+    const int64_t stride = (std::max<int64_t>(v.max_len, 1) + 7) & ~7ll;
+    int64_t nsub = std::max<int64_t>(1, (1ll << 30) / (16 * stride));      // <= 1 GiB per boundary buffer
+    nsub = std::min<int64_t>(nsub, v.n_reads);
+    TRY(ensure(s.bnd_a, (size_t)nsub * stride * sizeof(BndCell)));
+    TRY(ensure(s.bnd_b, (size_t)nsub * stride * sizeof(BndCell)));
+    for (int64_t r0 = 0; r0 < v.n_reads; r0 += nsub) {
+        const int64_t nr = std::min<int64_t>(nsub, v.n_reads - r0);
+        BndCell *cur = (BndCell *)s.bnd_a.p, *nxt = (BndCell *)s.bnd_b.p;
+        for (int b = 0; b < nb; b++) {
+            DtwArgs a{};
+            a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
+            a.offsets = v.offsets; a.read0 = v.read0 + r0; a.n_reads = (int)nr;
+            a.stats = (const ReadStats *)s.stats.p + r0;
+            a.model = d_model + (size_t)b * rows; a.N = std::min(rows, N - b * rows);
+            a.lo = clamp_lim(p->lo); a.hi = clamp_lim(p->hi);
+            a.hits = d_hits + r0 * hit_stride; a.hit_stride = hit_stride;
+            a.counter = d_counter;
+            a.bnd_in = b > 0 ? cur : nullptr;
+            a.bnd_out = b < nb - 1 ? nxt : nullptr;
+            a.bnd_stride = stride;
+            CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st));
+            const int K = (a.N + 31) / 32;
+            cudaError_t e = sqk_launch_dtw_f64_bnd_l32(K, a, c->n_sms, st);
+            if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW row-block launch (N=%d, block %d of %d, K=%d): %s", N, b, nb, K, cudaGetErrorString(e));
+            c->n_launches++;
+            std::swap(cur, nxt);
+        }
+    }
+    return SQK_OK;
+}
 
 // stats + the DTW of every model over a device-resident View; d_hits is [n_reads][n_models]
 static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, const double *d_models,
@@ -707,8 +745,25 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         const int N = h_model_offsets[m + 1] - h_model_offsets[m];
         int L = 0, K = 0;
         sqk_dtw_launcher fn = nullptr;
-        TRY(pick_dtw(c, N, p->precision, &L, &K, &fn));
+        if (N <= 32 * SQK_DTW_L32_KMAX) TRY(pick_dtw(c, N, p->precision, &L, &K, &fn));
         unsigned *ctr = (unsigned *)s.counter.p + (size_t)m * SQK_CTRS_PER_MODEL;
+        if (N > 32 * SQK_DTW_L32_KMAX) {
+            // ---- motif longer than one pass holds (mlpy takes any length; MotifSeq.py:382-405 expands a fasta to ~9 points
+            // per base): float64 row blocks, the last row of a block handed to the next one through a boundary row ---------
+            cudaEvent_t eb;
+            TRY(tick(c, SQK_K_DTW, st, &eb));
+            TRY(enqueue_long_motif(c, s, st, v, d_models + h_model_offsets[m], N, p, d_hits + m, n_models, ctr + 6));
+            if (publish && c->peers.n) {
+                PeerOut po{};
+                for (int q = 0; q < c->peers.n; q++) po.peer[po.n++] = c->peers.peer[q] + c->peer_base * n_models + m;
+                const unsigned pg = (unsigned)std::max<int64_t>(1, std::min<int64_t>((v.n_reads + 255) / 256, 2 * c->n_sms));
+                sqk_publish_kernel<<<pg, 256, 0, st>>>(d_hits + m, n_models, nullptr, nullptr, (int)v.n_reads, po);
+                CU(cudaGetLastError());
+                c->n_launches++;
+            }
+            TRY(tock(eb, st));
+            continue;
+        }
         DtwArgs a{};
         a.base = v.base; a.alloc_lo = v.alloc_lo; a.alloc_hi = v.alloc_hi;
         a.offsets = v.offsets; a.read0 = v.read0; a.n_reads = (int)v.n_reads;
@@ -1143,7 +1198,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
     for (int i = 0; i < 2; i++) {
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
-        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks); release(s.bnd_a); release(s.bnd_b);
         release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres); release(s.redo); release(s.mask);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);

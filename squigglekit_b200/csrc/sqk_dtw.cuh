@@ -42,6 +42,9 @@
 #endif
 #define SQK_DTW_MINB(K) ((K) <= 10 ? SQK_DTW_MINB_SMALLK : 1)
 
+// one cell of a boundary row between two row blocks: cost and start pointer as the recurrence carries them
+struct __align__(16) BndCell { double c; int s; int pad; };
+
 struct DtwArgs {
     const int16_t *base;      // base[i] = absolute sample i
     int64_t alloc_lo, alloc_hi;
@@ -61,6 +64,11 @@ struct DtwArgs {
     const unsigned int *n_jobs;   // how many (device memory: produced by the previous kernel)
     sqk_hit *job_out;         // job_out[job.out * job_out_stride]
     int job_out_stride;
+    // BND variant only (motifs longer than one pass holds: the rows are cut into blocks, sqk_api.cu): row r0 - 1 of the
+    // previous block for every column of every read comes in, the block's last row goes out
+    const BndCell *bnd_in;    // [n_reads][bnd_stride] or null: this is the first block (free-start row above)
+    BndCell *bnd_out;         // [n_reads][bnd_stride] or null: this is the last block (the hit is written)
+    int64_t bnd_stride;
 };
 
 template <typename T> struct DtwNum;
@@ -78,17 +86,26 @@ template <> struct DtwNum<float> {
 
 // One wavefront step of one lane: column (t - l) for this lane's K rows.  (ci, si) hold the previous
 // column of these rows, (co, so) receive the new one.
-template <typename T, int K, int L, bool RAGGED, bool JOBS>
+template <typename T, int K, int L, bool RAGGED, bool JOBS, bool BND = false>
 __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T (&co)[K], int (&so)[K],
                                          const T (&x)[K], const T *ring, int l, bool pass0, int t, int n_last,
                                          T &bot_c, int &bot_s, T &prev_up_c, int &prev_up_s,
-                                         T &best, int &best_j, int &best_s, int arg_lo, bool tainted)
+                                         T &best, int &best_j, int &best_s, int arg_lo, bool tainted,
+                                         const BndCell *bin = nullptr, BndCell *bout = nullptr, int n_cols = 0,
+                                         BndCell *pre = nullptr)
 {
     using Num = DtwNum<T>;
     constexpr int RC = 16 * L;
     T up_c = Num::shfl_up(bot_c, L);
     int up_s = __shfl_up_sync(SQK_FULL_MASK, bot_s, 1, L);
     if (l == 0) { up_c = (T)0; up_s = t + 1; }          // virtual row above row 0: free start
+    if constexpr (BND) {
+        if (l == 0 && bin != nullptr) {
+            // the row above this block's first row: column t was fetched during the previous step, t + 1 is requested now
+            up_c = (T)pre->c; up_s = pre->s;
+            if (t + 1 < n_cols) *pre = bin[t + 1];
+        }
+    }
     const T y = ring[(t - l) & (RC - 1)];
     T dg_c = prev_up_c; int dg_s = prev_up_s;
     prev_up_c = up_c; prev_up_s = up_s;
@@ -107,6 +124,12 @@ __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T
         co[k] = nc; so[k] = m_s;
     }
     bot_c = u_c; bot_s = u_s;
+    if constexpr (BND) {
+        if (bout != nullptr && l == L - 1 && (unsigned)(t - (L - 1)) < (unsigned)n_cols) {
+            BndCell o; o.c = (double)bot_c; o.s = bot_s; o.pad = 0;
+            bout[t - (L - 1)] = o;
+        }
+    }
     if constexpr (JOBS) {
         if (tainted && t == l) {
             // this lane just computed the window's boundary column: rows >= 1 become the strict lower bound -1 with
@@ -128,7 +151,7 @@ __device__ __forceinline__ void dtw_step(const T (&ci)[K], const int (&si)[K], T
     }
 }
 
-template <typename T, int K, int L, bool RAGGED, bool JOBS = false>
+template <typename T, int K, int L, bool RAGGED, bool JOBS = false, bool BND = false>
 __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kernel(const DtwArgs a)
 {
     constexpr int G = 32 / L;          // reads per warp
@@ -149,6 +172,9 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
     T *ring = ring_all + ((threadIdx.x >> 5) * G + g) * RC;
     for (int q = l; q < RC; q += L) ring[q] = (T)0;   // never leave non-finite garbage in the ring
     __syncwarp();
+    const BndCell *bin = nullptr;      // BND: this read's boundary rows
+    BndCell *bout = nullptr;
+    BndCell pre; pre.c = 0.0; pre.s = 0; pre.pad = 0;
 
     // motif rows of this lane
     const int P = L * K - a.N;                         // pass-through slots, 0 <= P < L
@@ -232,6 +258,15 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
                         for (int k = 0; k < K; k++) { c[k] = Num::inf(); s[k] = 0; }
                         bot_c = Num::inf(); bot_s = 0;
                         prev_up_c = (l == 0) ? (T)0 : Num::inf(); prev_up_s = 0;
+                        if constexpr (BND) {
+                            bin = a.bnd_in ? a.bnd_in + (int64_t)idx * a.bnd_stride : nullptr;
+                            bout = a.bnd_out ? a.bnd_out + (int64_t)idx * a.bnd_stride : nullptr;
+                            if (bin != nullptr) {
+                                prev_up_c = Num::inf();                    // no column in front of the first one
+                                if (l == 0) pre = bin[0];
+                            }
+                            if (bout != nullptr) n_last = 0;               // not the last block: no argmin, no hit
+                        }
                         best = Num::inf(); best_j = -1; best_s = -1;
                     }
                 }
@@ -298,9 +333,9 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
         //      so no register-to-register copies are needed to keep the previous column alive) ----
 #pragma unroll 1
         for (int it = 0; it < S; it += 2) {
-            dtw_step<T, K, L, RAGGED, JOBS>(c, s, c2, s2, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted);
+            dtw_step<T, K, L, RAGGED, JOBS, BND>(c, s, c2, s2, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted, bin, bout, n, &pre);
             t++;
-            dtw_step<T, K, L, RAGGED, JOBS>(c2, s2, c, s, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted);
+            dtw_step<T, K, L, RAGGED, JOBS, BND>(c2, s2, c, s, x, ring, l, pass0, t, n_last, bot_c, bot_s, prev_up_c, prev_up_s, best, best_j, best_s, arg_lo, tainted, bin, bout, n, &pre);
             t++;
         }
         __syncwarp();
@@ -313,7 +348,7 @@ __global__ void __launch_bounds__(SQK_DTW_THREADS, SQK_DTW_MINB(K)) sqk_dtw_kern
                     h.end = col0 + best_j;
                     a.job_out[(int64_t)my_read * a.job_out_stride] = h;
                 } else {
-                    a.hits[(int64_t)my_read * a.hit_stride] = h;
+                    if (!BND || bout == nullptr) a.hits[(int64_t)my_read * a.hit_stride] = h;
                 }
             }
             done = true;

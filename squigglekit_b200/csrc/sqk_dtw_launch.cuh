@@ -52,6 +52,35 @@ struct SqkDtwDispatch {
         return SqkDtwDispatch<T, L, KMIN, KMAX>::go(K, a, n_sms, st);                               \
     }
 
+// Row-block variant (motifs longer than one pass holds): float64, 32 lanes, rows cut into blocks by sqk_api.cu; one TU.
+template <int K, bool RAGGED>
+static cudaError_t sqk_dtw_launch_bnd(const DtwArgs &a, int n_sms, cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sqk_dtw_kernel<double, K, 32, RAGGED, false, true>, SQK_DTW_THREADS, 0);
+        if (e != cudaSuccess) return e;
+        occ = o > 0 ? o : 1;
+    }
+    long long want = ((long long)a.n_reads + SQK_DTW_WARPS - 1) / SQK_DTW_WARPS;
+    long long grid = (long long)n_sms * occ;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    sqk_dtw_kernel<double, K, 32, RAGGED, false, true><<<(unsigned)grid, SQK_DTW_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+template <int K, int KMAX>
+struct SqkDtwBndDispatch {
+    static cudaError_t go(int k, const DtwArgs &a, int n_sms, cudaStream_t st)
+    {
+        if (k == K) return a.N == K * 32 ? sqk_dtw_launch_bnd<K, false>(a, n_sms, st) : sqk_dtw_launch_bnd<K, true>(a, n_sms, st);
+        if constexpr (K < KMAX) return SqkDtwBndDispatch<K + 1, KMAX>::go(k, a, n_sms, st);
+        else return cudaErrorInvalidValue;
+    }
+};
+cudaError_t sqk_launch_dtw_f64_bnd_l32(int K, const DtwArgs &a, int n_sms, cudaStream_t st);
+
 // launchers defined across sqk_dtw_*.cu; [KMIN, KMAX] per lanes-per-read must match sqk_api.cu
 #define SQK_DTW_L1_KMIN 1
 #define SQK_DTW_L1_KMAX 4
@@ -71,7 +100,6 @@ struct SqkDtwDispatch {
     cudaError_t sqk_launch_dtw_##TAG##_l16(int, const DtwArgs &, int, cudaStream_t);           \
     cudaError_t sqk_launch_dtw_##TAG##_l32(int, const DtwArgs &, int, cudaStream_t);
 SQK_DECLARE_DTW_LAUNCHERS(f64)
-SQK_DECLARE_DTW_LAUNCHERS(f32)
 
 // pass 1 of the two-pass plan (sqk_dtw_lb.cuh), same (lanes, rows-per-lane) grid; defined in sqk_dtw_lb_l*.cu
 struct LbArgs;

@@ -8,9 +8,9 @@
 //     next read's bulk copy (cp.async.bulk + mbarrier) is issued before the current read is touched.
 //   * the pairwise tree (numpy's order, sqk_stats_plan.cuh) is walked from a DENSE list of leaves: one 32-bit word per
 //     leaf (shared address of its first sample | length | slot), built once per read with ballots.  Leaves that contain an
-//     outlier are copied, compacted, into a small patch area first, so the summation loop knows only one kind of leaf:
-//     a contiguous run of int16 at some 2-byte aligned address.  No per-sample exception handling, no divergence between
-//     "clean" and "unclean" teams.
+//     outlier are compacted in place first (inside their own span of the staged read; the exception list is rewritten to
+//     match), so the summation loop knows only one kind of leaf: a contiguous run of int16 at some 2-byte aligned
+//     address.  No per-sample exception handling, no divergence between "clean" and "unclean" teams, no side buffer.
 //   * the four 8-lane teams of the warp sum four leaves at a time, skewed by one row (16 bytes) per team: leaves lie
 //     256 bytes apart, so unskewed teams would always hit the same four banks.  Rows outside a team's leaf are predicated
 //     off; the loads themselves are unconditional (the layout keeps 64 bytes of slack in front of and 384 bytes behind
@@ -24,7 +24,6 @@
 #include "sqk_stats2.cuh"
 
 #define SQK_S3_MAXOUT 32            // outliers per read the exception list holds
-#define SQK_S3_PATCH 12             // leaves with an outlier inside that can be patched per read
 #define SQK_S3_SLOTS 128            // leaf slots: depth <= 7 for n <= 8192
 #define SQK_S3_MAX_LEN SQK_S2_MAX_LEN
 #define SQK_S3_MAX_BINS 2048
@@ -48,14 +47,14 @@ struct S3Shared {
     uint32_t list[SQK_S3_SLOTS + 4];    // dense leaf list: (shared address >> 1) | len << 17 | slot << 25, padded to a multiple of 4
     int out_pos[SQK_S3_MAXOUT];         // raw positions of the outliers (relative to the read's first sample), unsorted
     int out_adj[SQK_S3_MAXOUT];         // sorted, minus rank: outlier i sits in front of kept sample out_adj[i]
-    int patch_src[SQK_S3_PATCH][4];     // off, len, outliers in front
+    int patch_src[SQK_S3_MAXOUT][4];    // leaves with an outlier inside: off, len, outliers in front of / up to the end of the leaf
     int out_cnt, patch_cnt, pad0, pad1;
 };
 
 static inline size_t sqk_s3_smem_bytes(const Stats3Args &A)
 {
     return ((sizeof(S3Shared) + 15) & ~(size_t)15) + 4 * (size_t)(A.hist_words + A.mask_words) + SQK_S3_FRONT_SLACK +
-           256 * (size_t)SQK_S3_PATCH + SQK_S3_FRONT_SLACK + (size_t)A.buf_bytes + SQK_S3_BACK_SLACK;
+           (size_t)A.buf_bytes + SQK_S3_BACK_SLACK;
 }
 
 __device__ __forceinline__ int s3_lds_s16(unsigned addr)
@@ -64,37 +63,116 @@ __device__ __forceinline__ int s3_lds_s16(unsigned addr)
     asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// ++hist[v - wlo] by shared address (hist_b = shared address of the bin of raw value 0): two integer instructions + ATOMS
+__device__ __forceinline__ void s3_hist_inc(unsigned hist_b, int v)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_b + 4u * (unsigned)v) : "memory");
+}
 __device__ __forceinline__ void s3_sts_u16(unsigned addr, int v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((short)v) : "memory");
 }
 
-// Start staging a read into the buffer at shared address `bufs`; called by the whole warp.
-__device__ __forceinline__ void s3_stage(const StatsArgs &a, const S2Read &rd, unsigned bufs, unsigned bar, int64_t alloc_lo,
-                                         int64_t alloc_hi)
+// Start staging a read into the buffer at shared address `bufs`; called by the whole warp.  Only bulk copies: a read whose
+// 16-byte hull sticks out of the allocation (the first / last read of a buffer at most) goes to the redo list.
+__device__ __forceinline__ void s3_stage(const StatsArgs &a, const S2Read &rd, unsigned bufs, unsigned bar)
 {
-    if (rd.units == 0) return;
-    const int lane = threadIdx.x;
-    const int16_t *src = a.base + (rd.begin - rd.h0);
-    if (rd.tma) {
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to the buffer
-            s2_mbar_expect_tx(bar, (unsigned)rd.units * 16u);
-            s2_bulk_g2s(bufs, src, (unsigned)rd.units * 16u, bar);
-        }
-    } else {
-        for (int u = lane; u < rd.units; u += 32) {
-            const Samples8 sv = load_block8(a.base, rd.begin - rd.h0 + 8ll * u, alloc_lo, alloc_hi);
-            s2_sts128(bufs + 16u * (unsigned)u, sv.v);
-        }
+    if (rd.units == 0 || !rd.tma) return;
+    if (threadIdx.x == 0) {
+        const int16_t *src = a.base + (rd.begin - rd.h0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to the buffer
+        s2_mbar_expect_tx(bar, (unsigned)rd.units * 16u);
+        s2_bulk_g2s(bufs, src, (unsigned)rd.units * 16u, bar);
     }
 }
 
-// One round of the leaf summation for this lane: rows i - team of the leaf whose first sample (for this lane: + 2k bytes,
-// - 16 * team bytes of skew) sits at `base`; bit i of `rows_mask` says whether skewed row i is a row of the leaf.
-// FULL: all four teams of the warp have a 16-row leaf, so skewed rows 3..15 are rows of every team's leaf and need no
-// predicate.  The predicated add is spelled in PTX: the compiler would turn `if (bit) acc += t` into an add and two
-// selects.
+// Rare paths, out of line: the kernel's hot code has to stay small (one-warp CTAs at different places of a long
+// straight-line kernel share the instruction cache; the first version stalled on instruction fetch more than on data).
+
+// a 16-byte unit with outliers inside: only the flagged words are looked at, half by half
+template <bool HIST>
+__device__ __noinline__ int s3_unit_outliers(int4 wq, int4 dq, int pos0, int *out_cnt, int *out_pos, uint32_t *hist_m)
+{
+    const int w[4] = {wq.x, wq.y, wq.z, wq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
+    int sub = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int vl = (int)(short)(w[e] & 0xffff), vh = w[e] >> 16;
+        if (dw[e] & 0xffff) {
+            sub += vl;
+            const int at = atomicAdd(out_cnt, 1);
+            if (at < SQK_S3_MAXOUT) out_pos[at] = pos0 + 2 * e;
+        } else if (HIST) atomicAdd(hist_m + vl, 1u);
+        if (dw[e] & 0xffff0000) {
+            sub += vh;
+            const int at = atomicAdd(out_cnt, 1);
+            if (at < SQK_S3_MAXOUT) out_pos[at] = pos0 + 2 * e + 1;
+        } else if (HIST) atomicAdd(hist_m + vh, 1u);
+    }
+    return sub;                                         // what the packed sum has to lose again
+}
+
+// Leaves with an outlier inside are compacted IN PLACE: the kept samples of such a leaf are moved to the front of the
+// leaf's own span of the staged read (they start where the leaf's first kept sample already is), which leaves as many
+// stale slots at the end of the span as it had outliers.  Afterwards every leaf is a contiguous run again, and the
+// exception list is rewritten to say so: the leaf's outliers now sit in front of the kept sample that follows the leaf.
+// (Leaves are at most 128 samples: four per lane, all loads before any store.)
+__device__ __noinline__ void s3_patch_in_place(S3Shared &sh, int n_patch, unsigned bufs, int h0)
+{
+    const int lane = threadIdx.x;
+    for (int pi = 0; pi < n_patch; pi++) {
+        const int off = sh.patch_src[pi][0], ln = sh.patch_src[pi][1], c0 = sh.patch_src[pi][2], c1 = sh.patch_src[pi][3];
+        const int adj0 = sh.out_adj[c0], adj1 = c1 - c0 > 1 ? sh.out_adj[c0 + 1] : 0x7fffffff;   // nearly always one or two
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = lane + 32 * q;
+            v[q] = 0;
+            if (c < ln) {
+                const int g = off + c;
+                int shf = c0 + ((adj0 <= g) ? 1 : 0) + ((adj1 <= g) ? 1 : 0);
+                for (int j = c0 + 2; j < c1; j++) shf += (sh.out_adj[j] <= g) ? 1 : 0;
+                v[q] = s2_lds_s16(bufs + 2u * (unsigned)(h0 + g + shf));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = lane + 32 * q;
+            if (c < ln) s3_sts_u16(bufs + 2u * (unsigned)(h0 + off + c0 + c), v[q]);
+        }
+        __syncwarp();
+    }
+    // (after all leaves: a leaf's rewrite must not change what a later leaf's search sees -- entries only move to
+    // positions <= the next leaf's first index, so doing it at the end is merely simpler to reason about)
+    for (int pi = 0; pi < n_patch; pi++) {
+        const int off = sh.patch_src[pi][0], ln = sh.patch_src[pi][1], c0 = sh.patch_src[pi][2], c1 = sh.patch_src[pi][3];
+        for (int j = c0 + lane; j < c1; j += 32) sh.out_adj[j] = off + ln;
+    }
+    __syncwarp();
+}
+
+// compacted mask word of kept samples [c0, clast] when outliers sit inside: one funnel shift per piece between them
+__device__ __noinline__ uint32_t s3_mask_pieces(const S3Shared &sh, const uint32_t *rawmask, int n_out, int h0, int c0, int clast, int s0)
+{
+    uint32_t wv = 0;
+    int c = c0, sft = s0;
+    while (c <= clast) {
+        while (sft < n_out && sh.out_adj[sft] <= c) sft++;     // outliers in front of kept sample c
+        int stop = clast + 1;                                   // first kept sample of the next piece
+        if (sft < n_out && sh.out_adj[sft] <= clast) stop = sh.out_adj[sft];
+        const int R = h0 + c + sft;
+        uint32_t piece = __funnelshift_r(rawmask[R >> 5], rawmask[(R >> 5) + 1], R & 31);
+        const int plen = stop - c;
+        if (plen < 32) piece &= (1u << plen) - 1u;
+        wv |= piece << (c - c0);
+        c = stop;
+    }
+    return wv;
+}
+
+// Leaf rows of one round.  FULL: all four teams of the warp have a 16-row leaf, so skewed rows 3..15 are rows of every
+// team's leaf and need no predicate; otherwise every row is predicated.
 template <bool FULL, class Term>
 __device__ __forceinline__ double s3_rows(Term term, unsigned base, unsigned rows_mask)
 {
@@ -103,9 +181,7 @@ __device__ __forceinline__ double s3_rows(Term term, unsigned base, unsigned row
     for (int i = 0; i < 19; i++) {
         const double t = term(s3_lds_s16(base + 16u * (unsigned)i));
         if (FULL && i >= 3 && i < 16) acc = __dadd_rn(acc, t);
-        else
-            asm("{\n\t.reg .pred p;\n\t.reg .b32 m;\n\tand.b32 m, %2, %3;\n\tsetp.ne.u32 p, m, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
-                : "+d"(acc) : "d"(t), "r"(rows_mask), "r"(1u << i));
+        else if (rows_mask & (1u << i)) acc = __dadd_rn(acc, t);
     }
     return acc;
 }
@@ -132,8 +208,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
     constexpr bool WANT_SD = (MODE == SQK_STATS_ZSCALE || MODE == SQK_STATS_SEGMENTER);
     uint32_t *hist = reinterpret_cast<uint32_t *>(s3_smem + FIXED);
     uint32_t *rawmask = hist + A.hist_words;
-    const unsigned patch = s2_smem_addr(rawmask + A.mask_words) + SQK_S3_FRONT_SLACK;
-    const unsigned bufs = patch + 256u * SQK_S3_PATCH + SQK_S3_FRONT_SLACK;
+    const unsigned bufs = s2_smem_addr(rawmask + A.mask_words) + SQK_S3_FRONT_SLACK;
     const unsigned bar = s2_smem_addr(&sh.bar[0]);
 
     const int lane = threadIdx.x, team = lane >> 3, k = lane & 7;
@@ -157,6 +232,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
     const int lo2 = (wlo & 0xffff) | (wlo << 16), hi2 = (whi & 0xffff) | (whi << 16);
     const unsigned span = (unsigned)(whi - wlo);
     uint32_t *const hist_m = hist - wlo;                      // the bin of raw value 0
+    const unsigned hist_b = s2_smem_addr(hist) - 4u * (unsigned)wlo;
 
     // One staging buffer per warp (shared memory per warp, not the copy engine, limits the warps per SM, and this kernel
     // needs warps: its phases are dependent chains).  The next read's bulk copy is issued as soon as the last pass over
@@ -167,7 +243,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
     S2Read rd{};
     if (i < a.n_reads) {
         rd = s2_describe(a, i, alloc_lo, alloc_hi, A.buf_bytes);
-        s3_stage(a, rd, bufs, bar, alloc_lo, alloc_hi);
+        s3_stage(a, rd, bufs, bar);
     }
     for (; i < a.n_reads; i += stride) {
         const int64_t inext = i + stride;
@@ -177,18 +253,16 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
         auto stage_next = [&]() {
             if (!staged_next && inext < a.n_reads) {
                 __syncwarp();                                   // every lane is done with the staged samples
-                s3_stage(a, nx, bufs, bar, alloc_lo, alloc_hi);
+                s3_stage(a, nx, bufs, bar);
             }
             staged_next = true;
         };
         if (rd.units > 0 && rd.tma) {
             s2_mbar_wait(bar, uses & 1u);
             uses++;
-        } else {
-            __syncwarp();                                       // thread-staged: the other lanes' stores
         }
 
-        const bool punt = !rd.ok || !window_ok || !hist_ok;     // not for this kernel: the redo list takes it
+        const bool punt = !rd.ok || !rd.tma || !window_ok || !hist_ok;     // not for this kernel: the redo list takes it
         const int h0 = rd.h0, len = rd.len;
         // ---- phase A: window test, integer sum, histogram, outlier list --------------------------------------------
         int lsum = 0;
@@ -207,26 +281,12 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
                     if (HIST) {
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            atomicAdd(hist_m + (int)(short)(w[e] & 0xffff), 1u);
-                            atomicAdd(hist_m + (w[e] >> 16), 1u);
+                            s3_hist_inc(hist_b, (int)(short)(w[e] & 0xffff));
+                            s3_hist_inc(hist_b, w[e] >> 16);
                         }
                     }
                 } else {
-                    // rare: a unit with outliers; only the flagged words are looked at half by half
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int vl = (int)(short)(w[e] & 0xffff), vh = w[e] >> 16;
-                        if (dw[e] & 0xffff) {
-                            lsum -= vl;
-                            const int at = atomicAdd(&sh.out_cnt, 1);
-                            if (at < SQK_S3_MAXOUT) sh.out_pos[at] = 8 * u + 2 * e - h0;
-                        } else if (HIST) atomicAdd(hist_m + vl, 1u);
-                        if (dw[e] & 0xffff0000) {
-                            lsum -= vh;
-                            const int at = atomicAdd(&sh.out_cnt, 1);
-                            if (at < SQK_S3_MAXOUT) sh.out_pos[at] = 8 * u + 2 * e + 1 - h0;
-                        } else if (HIST) atomicAdd(hist_m + vh, 1u);
-                    }
+                    lsum -= s3_unit_outliers<HIST>(q, make_int4(dw[0], dw[1], dw[2], dw[3]), 8 * u - h0, &sh.out_cnt, sh.out_pos, hist_m);   // rare
                 }
             }
             // the (at most 7 + 7) samples in front of / behind the whole units: one lane each
@@ -284,14 +344,10 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
                         c0 += (adj <= off) ? 1 : 0;
                         c1 += (adj <= off + ln - 1) ? 1 : 0;
                     }
-                    if (c0 == c1) {
-                        addr = bufs + 2u * (unsigned)(h0 + off + c0);
-                    } else {
-                        const int pi = atomicAdd(&sh.patch_cnt, 1);
-                        if (pi < SQK_S3_PATCH) {
-                            sh.patch_src[pi][0] = off; sh.patch_src[pi][1] = ln; sh.patch_src[pi][2] = c0; sh.patch_src[pi][3] = c1;
-                            addr = patch + 256u * (unsigned)pi;
-                        }
+                    addr = bufs + 2u * (unsigned)(h0 + off + c0);   // (a leaf with outliers inside is compacted in place below)
+                    if (c0 != c1) {
+                        const int pi = atomicAdd(&sh.patch_cnt, 1);    // <= n_out <= SQK_S3_MAXOUT
+                        sh.patch_src[pi][0] = off; sh.patch_src[pi][1] = ln; sh.patch_src[pi][2] = c0; sh.patch_src[pi][3] = c1;
                     }
                 }
                 const unsigned m = __ballot_sync(SQK_FULL_MASK, mine);
@@ -302,21 +358,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
             if (lane < 3) sh.list[n_leaves + lane] = bufs >> 1;           // empty entries: len 0
             __syncwarp();
             const int n_patch = sh.patch_cnt;
-            if (n_patch > SQK_S3_PATCH) redo = true;
-            else {
-                for (int pi = 0; pi < n_patch; pi++) {
-                    const int off = sh.patch_src[pi][0], ln = sh.patch_src[pi][1], c0 = sh.patch_src[pi][2], c1 = sh.patch_src[pi][3];
-                    // the outliers inside this leaf: nearly always one or two
-                    const int adj0 = sh.out_adj[c0], adj1 = c1 - c0 > 1 ? sh.out_adj[c0 + 1] : 0x7fffffff;
-                    for (int c = lane; c < ln; c += 32) {
-                        const int g = off + c;
-                        int shf = c0 + ((adj0 <= g) ? 1 : 0) + ((adj1 <= g) ? 1 : 0);
-                        for (int j = c0 + 2; j < c1; j++) shf += (sh.out_adj[j] <= g) ? 1 : 0;
-                        s3_sts_u16(patch + 256u * (unsigned)pi + 2u * (unsigned)c, s2_lds_s16(bufs + 2u * (unsigned)(h0 + g + shf)));
-                    }
-                }
-                if (n_patch) __syncwarp();
-            }
+            if (n_patch) s3_patch_in_place(sh, n_patch, bufs, h0);
         }
 
         ReadStats out;
@@ -422,48 +464,37 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
                     out.seg_lo = seg_lo; out.seg_hi = seg_hi;
                     out.center = top; out.scale = bot;
                 }
+                // the packed in-range test needs the window span to fit a signed 16-bit lane; wider windows (thresholds
+                // further apart than half the int16 range) are left to the first-generation kernel
+                const int slo = seg_lo < -32768 ? -32768 : seg_lo, shi = seg_hi > 32767 ? 32767 : seg_hi;
+                const bool any = shi >= slo && n > 0;
+                const int sspan = shi - slo;
+                if (A.mask && !redo && any && sspan > 32766) redo = true;
                 if (A.mask && !redo) {
                     // raw-space in-range bits, one 32-bit word per 4 units (bit B = buffer sample B)
-                    const int slo = seg_lo < -32768 ? -32768 : seg_lo, shi = seg_hi > 32767 ? 32767 : seg_hi;
-                    const bool any = shi >= slo && n > 0;
-                    const int sspan = shi - slo;
                     const int raw_words = (rd.units + 3) >> 2;
-                    if (any && sspan <= 32766) {
-                        const unsigned negslo2 = ((unsigned)(-slo) & 0xffffu) * 0x10001u;
-                        const unsigned lim2 = (unsigned)(sspan + 1) * 0x10001u;
-                        const unsigned negspan2 = ((unsigned)(-sspan) & 0xffffu) * 0x10001u;
-                        for (int wd = lane; wd <= raw_words; wd += 32) {
-                            uint32_t acc = 0;
-                            if (wd < raw_words) {
+                    const unsigned negslo2 = ((unsigned)(-slo) & 0xffffu) * 0x10001u;
+                    const unsigned lim2 = (unsigned)((sspan + 1) & 0xffff) * 0x10001u;
+                    const unsigned negspan2 = ((unsigned)(-sspan) & 0xffffu) * 0x10001u;
+                    for (int wd = lane; wd <= raw_words; wd += 32) {
+                        uint32_t acc = 0;
+                        if (any && wd < raw_words) {
 #pragma unroll
-                                for (int uu = 0; uu < 4; uu++) {
-                                    // (units behind the read's last one are inside the buffer or the slack behind it)
-                                    const int4 q = s2_lds128(bufs + 16u * (unsigned)(4 * wd + uu));
-                                    const unsigned w[4] = {(unsigned)q.x, (unsigned)q.y, (unsigned)q.z, (unsigned)q.w};
+                            for (int uu = 0; uu < 4; uu++) {
+                                // (units behind the read's last one are inside the buffer or the slack behind it)
+                                const int4 q = s2_lds128(bufs + 16u * (unsigned)(4 * wd + uu));
+                                const unsigned w[4] = {(unsigned)q.x, (unsigned)q.y, (unsigned)q.z, (unsigned)q.w};
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) {
-                                        // per half: min(v - slo mod 2^16, span + 1) - span, floored at 0  ->  1 = out of range
-                                        const unsigned t = __viaddmin_u16x2(w[e], negslo2, lim2);
-                                        const unsigned o = __viaddmax_s16x2_relu(t, negspan2, 0u);
-                                        acc += o << (4 * uu + e);        // even samples -> bits 0..15, odd -> 16..31
-                                    }
-                                }
-                                acc = ~s3_interleave16(acc);
-                            }
-                            rawmask[wd] = acc;
-                        }
-                    } else {
-                        const unsigned ssp = (unsigned)sspan;
-                        for (int wd = lane; wd <= raw_words; wd += 32) {
-                            uint32_t bits = 0;
-                            if (any && wd < raw_words) {
-                                for (int e = 0; e < 32; e++) {
-                                    const int v = s2_lds_s16(bufs + 2u * (unsigned)(32 * wd + e));
-                                    if ((unsigned)(v - slo) <= ssp) bits |= 1u << e;
+                                for (int e = 0; e < 4; e++) {
+                                    // per half: min(v - slo mod 2^16, span + 1) - span, floored at 0  ->  1 = out of range
+                                    const unsigned t = __viaddmin_u16x2(w[e], negslo2, lim2);
+                                    const unsigned o = __viaddmax_s16x2_relu(t, negspan2, 0u);
+                                    acc += o << (4 * uu + e);        // even samples -> bits 0..15, odd -> 16..31
                                 }
                             }
-                            rawmask[wd] = bits;
+                            acc = ~s3_interleave16(acc);
                         }
+                        rawmask[wd] = acc;
                     }
                     stage_next();                               // (syncs the warp) the staged samples are not read again
                     // compacted word t holds kept samples [32t, 32t+32): a funnel shift of the raw-space words unless an
@@ -485,19 +516,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
                                 const int R = h0 + c0 + s0;
                                 wv = __funnelshift_r(rawmask[R >> 5], rawmask[(R >> 5) + 1], R & 31);
                             } else {
-                                // outliers inside: one funnel shift per piece between them
-                                int c = c0, sft = s0;
-                                while (c <= clast) {
-                                    while (sft < n_out && sh.out_adj[sft] <= c) sft++;     // outliers in front of kept sample c
-                                    int stop = clast + 1;                                   // first kept sample of the next piece
-                                    if (sft < n_out && sh.out_adj[sft] <= clast) stop = sh.out_adj[sft];
-                                    const int R = h0 + c + sft;
-                                    uint32_t piece = __funnelshift_r(rawmask[R >> 5], rawmask[(R >> 5) + 1], R & 31);
-                                    const int plen = stop - c;
-                                    if (plen < 32) piece &= (1u << plen) - 1u;
-                                    wv |= piece << (c - c0);
-                                    c = stop;
-                                }
+                                wv = s3_mask_pieces(sh, rawmask, n_out, h0, c0, clast, s0);
                             }
                             const int valid = n - c0;
                             if (valid < 32) wv &= (1u << valid) - 1u;

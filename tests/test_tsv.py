@@ -31,6 +31,8 @@ def test_round_trip(tmp_path, start_col, gz):
     with tsv.Reader(str(path), start_col, max_lines=37, max_samples=40000, block_bytes=30000, pinned=False) as rd:
         for b in rd:
             assert not b.status.any()
+            assert b.heads(2) == [b.head(i)[:2] for i in range(b.n)]      # one C call for the batch == line by line
+            assert b.heads(1) == [b.head(i)[:1] for i in range(b.n)]
             for i in range(b.n):
                 got_reads.append(b.sig(i).copy()); got_heads.append("\t".join(b.head(i)))
     assert got_heads == heads
