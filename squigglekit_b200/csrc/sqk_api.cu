@@ -161,7 +161,7 @@ struct sqk_ctx {
     int64_t chunk_samples = 0;     // host mode: samples per in-flight chunk (0 = default / SQK_CHUNK_SAMPLES)
     int stats_smem_set32 = -1, stats_smem_set128 = -1, stats_smem_set256 = -1;
     int stats2_smem_set[5] = {-1, -1, -1, -1, -1};
-    int stats3_smem_set[3] = {-1, -1, -1};
+    int stats3_smem_set[4] = {-1, -1, -1, -1};
     int stats_gen = 0;                // 0 = automatic, 1 = first-generation kernel only (experiments / tests)
     // device-mode calls share the ctx scratch in stream order: the end of every enqueue is marked with an event and a
     // call that arrives on a different stream waits for it first
@@ -497,7 +497,7 @@ static int launch_stats3(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, con
     A.buf_bytes = ((cap_units + 15) / 16) * 256;
     const int lo1 = std::max(a.lo + 1, -32768), hi1 = std::min(a.hi - 1, 32767);
     const int nbins = hi1 >= lo1 ? hi1 - lo1 + 1 : 0;
-    A.hist_words = a.mode == SQK_STATS_SEGMENTER ? std::max(128, (nbins + 127) & ~127) : 0;
+    A.hist_words = (a.mode == SQK_STATS_SEGMENTER || a.mode == SQK_STATS_MEDMAD) ? std::max(128, (nbins + 127) & ~127) : 0;
     A.mask_words = want_mask ? ((A.buf_bytes / 64 + 2 + 3) & ~3) : 0;
     A.mask_stride = 0;
     if (want_mask) {
@@ -516,6 +516,7 @@ static int launch_stats3(sqk_ctx *c, Slot &s, cudaStream_t st, StatsArgs &a, con
     switch (a.mode) {
     case SQK_STATS_ZSCALE: kern = sqk_stats3_kernel<SQK_STATS_ZSCALE>; which = 0; break;
     case SQK_STATS_NONE: kern = sqk_stats3_kernel<SQK_STATS_NONE>; which = 1; break;
+    case SQK_STATS_MEDMAD: kern = sqk_stats3_kernel<SQK_STATS_MEDMAD>; which = 3; break;
     default: kern = sqk_stats3_kernel<SQK_STATS_SEGMENTER>; which = 2; break;
     }
     if (dyn > c->stats3_smem_set[which]) {
@@ -559,9 +560,9 @@ static int launch_stats(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v, int
     StatsOut local;
     if (gen != 1 && mode != SQK_STATS_ADAPTER && v.max_len <= SQK_S2_MAX_LEN && v.n_reads < 0x7ffffff0LL) {
         // third generation (one warp per read) where it applies: raw-integer zscale / segmenter / none, histogram-sized window
-        const bool s3_mode = mode == SQK_STATS_ZSCALE || mode == SQK_STATS_NONE || (mode == SQK_STATS_SEGMENTER && d_pa_off == nullptr);
+        const bool s3_mode = mode == SQK_STATS_ZSCALE || mode == SQK_STATS_NONE || mode == SQK_STATS_MEDMAD || (mode == SQK_STATS_SEGMENTER && d_pa_off == nullptr);
         const int64_t span = (int64_t)std::min(hi - 1, 32767) - std::max(lo + 1, -32768) + 1;
-        if (gen != 2 && s3_mode && (mode != SQK_STATS_SEGMENTER || span <= SQK_S3_MAX_BINS))
+        if (gen != 2 && s3_mode && ((mode != SQK_STATS_SEGMENTER && mode != SQK_STATS_MEDMAD) || span <= SQK_S3_MAX_BINS))
             return launch_stats3(c, s, st, a, v, want_mask, so ? so : &local);
         return launch_stats2(c, s, st, a, v, want_mask, so ? so : &local);
     }

@@ -1,5 +1,5 @@
 // sqk_stats3.cuh -- K1, third generation: ONE WARP PER READ, for reads of up to SQK_S3_MAX_LEN samples in the zscale,
-// segmenter (raw-integer) and "none" modes.  Same outputs, bit for bit, as sqk_stats_kernel / sqk_stats2_kernel.
+// medmad, segmenter (raw-integer) and "none" modes.  Same outputs, bit for bit, as sqk_stats_kernel / sqk_stats2_kernel.
 //
 // What changed against the second generation (profiles/r02_stats2_*: 5.5 k warp-instructions per 4096-sample read in
 // zscale mode, 9.5 k in segmenter mode, 21-24 of 32 lanes active, six CTA barriers per read):
@@ -152,6 +152,24 @@ __device__ __noinline__ void s3_patch_in_place(S3Shared &sh, int n_patch, unsign
     __syncwarp();
 }
 
+// A read with more outliers than the exception list holds (rare): compact the whole staged read in place, 32 samples per
+// step (kept samples only move towards the front, and a step's loads are done before its stores).  Afterwards it is a read
+// without outliers.
+__device__ __noinline__ void s3_compact_all(unsigned bufs, int h0, int len, int wlo, unsigned span)
+{
+    const int lane = threadIdx.x;
+    int wpos = 0;
+    for (int p0 = 0; p0 < len; p0 += 32) {
+        const int p = p0 + lane;
+        const int v = p < len ? s2_lds_s16(bufs + 2u * (unsigned)(h0 + p)) : 0;
+        const bool keep = p < len && (unsigned)(v - wlo) <= span;
+        const unsigned m = __ballot_sync(SQK_FULL_MASK, keep);
+        if (keep) s3_sts_u16(bufs + 2u * (unsigned)(h0 + wpos + __popc(m & ((1u << lane) - 1u))), v);
+        wpos += __popc(m);
+        __syncwarp();
+    }
+}
+
 // compacted mask word of kept samples [c0, clast] when outliers sit inside: one funnel shift per piece between them
 __device__ __noinline__ uint32_t s3_mask_pieces(const S3Shared &sh, const uint32_t *rawmask, int n_out, int h0, int c0, int clast, int s0)
 {
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
     extern __shared__ __align__(16) unsigned char s3_smem[];
     S3Shared &sh = *reinterpret_cast<S3Shared *>(s3_smem);
     constexpr unsigned FIXED = (sizeof(S3Shared) + 15) & ~15u;
-    constexpr bool HIST = (MODE == SQK_STATS_SEGMENTER);
+    constexpr bool HIST = (MODE == SQK_STATS_SEGMENTER || MODE == SQK_STATS_MEDMAD);
     constexpr bool WANT_SD = (MODE == SQK_STATS_ZSCALE || MODE == SQK_STATS_SEGMENTER);
     uint32_t *hist = reinterpret_cast<uint32_t *>(s3_smem + FIXED);
     uint32_t *rawmask = hist + A.hist_words;
@@ -311,9 +329,14 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
         __syncwarp();
         const int tot_sum = __reduce_add_sync(SQK_FULL_MASK, lsum);    // |sum| <= 8176 * 32768 < 2^31
         const int n_out_all = punt ? 0 : sh.out_cnt;
-        bool redo = punt || n_out_all > SQK_S3_MAXOUT;
-        const int n_out = redo ? 0 : n_out_all;
-        const int n = redo ? 0 : len - n_out;
+        bool redo = punt;
+        int n_out = redo ? 0 : n_out_all;
+        const int n = redo ? 0 : len - n_out_all;
+        if (n_out > SQK_S3_MAXOUT) {                            // rare: too many for the exception list
+            s3_compact_all(bufs, h0, len, wlo, span);
+            n_out = 0;
+        }
+        if constexpr (!WANT_SD) stage_next();                  // medmad / none: the staged samples are not read again
 
         if (n_out > 0) {
             if (lane < n_out) {
@@ -404,8 +427,58 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
             sd = __dsqrt_rn(__ddiv_rn(r, (double)n));
         }
 
+        // ---- medmad: median and MAD from the histogram, turned into prefix sums in place ---------------------------------
+        if constexpr (MODE == SQK_STATS_MEDMAD) {
+            if (!punt) {
+                const int groups = A.hist_words >> 7;           // chunks of 128 bins: lane owns bins 128 c + 4 lane .. + 4
+                int carry = 0;
+                for (int c = 0; c < groups; c++) {
+                    uint4 w = *reinterpret_cast<const uint4 *>(hist + 128 * c + 4 * lane);
+                    w.y += w.x; w.z += w.y; w.w += w.z;
+                    int incl = (int)w.w;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int tt = __shfl_up_sync(SQK_FULL_MASK, incl, dd);
+                        if (lane >= dd) incl += tt;
+                    }
+                    const unsigned add = (unsigned)(carry + incl) - w.w;
+                    w.x += add; w.y += add; w.z += add; w.w += add;
+                    *reinterpret_cast<uint4 *>(hist + 128 * c + 4 * lane) = w;
+                    carry += __shfl_sync(SQK_FULL_MASK, incl, 31);
+                }
+                __syncwarp();
+                if (n > 0 && !redo) {
+                    // every lane runs the same searches on the prefix sums (broadcast loads)
+                    auto P = [hist, nbins](int b) -> int { return b < 0 ? 0 : (int)hist[b < nbins ? b : nbins - 1]; };
+                    auto kth = [&P, nbins](int r) -> int {          // smallest bin b with P(b) > r
+                        int lo = 0, hi = nbins - 1;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P(mid) > r) hi = mid; else lo = mid + 1; }
+                        return lo;
+                    };
+                    const int r0 = (n - 1) >> 1, r1 = n >> 1;
+                    const int b0 = kth(r0), b1 = P(b0) > r1 ? b0 : kth(r1);
+                    const int med2 = 2 * wlo + b0 + b1, par = med2 & 1;              // doubled median, its parity
+                    const int lo_b = (med2 - par) / 2 - wlo, hi_b = (med2 + par) / 2 - wlo;
+                    // samples with |2v - med2| <= 2t + par  <=>  bins [lo_b - t, hi_b + t]
+                    auto within = [&P, lo_b, hi_b](int t) -> int { return P(hi_b + t) - P(lo_b - t - 1); };
+                    auto tth = [&within, nbins](int r) -> int {
+                        int lo = 0, hi = nbins;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (within(mid) > r) hi = mid; else lo = mid + 1; }
+                        return lo;
+                    };
+                    const int t0 = tth(r0), t1 = within(t0) > r1 ? t0 : tth(r1);
+                    const int d0 = 2 * t0 + par, d1 = 2 * t1 + par;                // the two middle doubled distances
+                    const double scaled = __dmul_rn((double)(d0 + d1) * 0.25, 1.4826);
+                    out.center = (double)med2 * 0.5; out.scale = scaled;
+                    if (scaled == 0.0) out.flags |= SQK_FLAG_DEGENERATE;
+                }
+                __syncwarp();
+                for (int g = lane; g < (A.hist_words >> 2); g += 32) *reinterpret_cast<uint4 *>(hist + 4 * g) = make_uint4(0, 0, 0, 0);
+            }
+        }
+
         // ---- segmenter: the median from the histogram (zeroed on the way), thresholds, in-range bit mask -----------
-        if constexpr (HIST) {
+        if constexpr (MODE == SQK_STATS_SEGMENTER) {
             if (!punt) {
                 const int groups = A.hist_words >> 7;           // chunks of 128 bins: lane owns bins 128 c + 4 lane .. + 4
                 const int ranks[2] = {(n - 1) >> 1, n >> 1};

@@ -277,7 +277,7 @@ def test_argument_errors_are_reported_not_crashed(ctx):
         ctx.motifseq(sig, off[::-1].copy(), motif)                                   # offsets not monotone
     assert ei.value.code == -1
     with pytest.raises(sqk.SqkError) as ei:
-        ctx.motifseq(sig, off, np.zeros(2000))                                       # motif longer than supported
+        ctx.motifseq(sig, off, [motif] * 300)                                        # more models than one call takes
     assert ei.value.code == -4
     with pytest.raises(sqk.SqkError):
         ctx.segmenter(sig, off, sqk.SegConfig(corrector=-1))
