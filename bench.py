@@ -292,7 +292,7 @@ def segmenter_block(ctx, dev, peak, steps):
         stats_ms = kt["stats"]["ms"] / max(1, kt["stats"]["launches"])
         fsm_ms = kt["seg_fsm"]["ms"] / max(1, kt["seg_fsm"]["launches"])
         run = {"reads": R, "value": R / (ms * 1e-3), "ms_per_step": ms,
-               "kernels_ms": {"stats (sqk_stats2_kernel + redo list)": stats_ms, "state machine (sqk_fsm_mask_kernel + redo list)": fsm_ms},
+               "kernels_ms": {"stats (sqk_stats3_kernel + redo list)": stats_ms, "state machine (sqk_fsm_mask_kernel + redo list)": fsm_ms},
                "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "algorithmic_bytes_per_read": SEG_BYTES_PER_READ,
                             "achieved_step": R * SEG_BYTES_PER_READ / (ms * 1e-3) / 1e9,
                             "frac_step": R * SEG_BYTES_PER_READ / (ms * 1e-3) / 1e9 / peak,
@@ -696,7 +696,8 @@ def main():
                        "dtw_lanes_per_read": args.lanes or "auto", "dtw_plan": args.plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr.get("dram_bytes_per_launch_100k_reads_lb" if two_pass else "dram_bytes_per_launch_100k_reads"),
-                         "traffic_source": tr.get("source") if tr else None,
+                         "traffic_source": (tr.get("lb_source") if two_pass else tr.get("source")) if tr else None,
+                         "traffic_note": "from a committed ncu capture of the same kernel and shape, not measured in this run" if tr else None,
                          "step_traffic_bytes": tr.get("dram_bytes_per_step_100k_reads_two_pass") if two_pass else None,
                          "step_algorithmic_bytes": R * BYTES_PER_READ,
                          "peak_source": peak_src, "kernel": kname,
