@@ -708,6 +708,7 @@ def main():
                          "exact_windows_ms_per_step": win_ms},
             "plan": {"name": "two_pass" if two_pass else "single_pass",
                      "exact_windows_per_step": plan_counters["windows"] if two_pass else None,
+                     "second_attempt_windows_per_step": plan_counters.get("second_attempt_windows") if two_pass else None,
                      "full_length_fallback_reads_per_step": plan_counters["fallback_reads"] if two_pass else None},
             "roofline_alu": {"achieved_cells_per_s": cells_s, "issue_ceiling_cells_per_s": issue_ceiling,
                              "frac": cells_s / issue_ceiling,

@@ -293,6 +293,8 @@ SQK_API int sqk_ctx_set_dtw_plan(sqk_ctx *ctx, int plan);
 /* Diagnostics of the most recent two-pass launch of slot 0 (device-mode calls; the last chunk in host mode), first
  * model: out[0] = exact windows run, out[1] = reads re-run over their full length.  Synchronises. */
 SQK_API int sqk_ctx_get_plan_counters(sqk_ctx *ctx, int64_t out[2]);
+/* the same plus out[2] = second-attempt windows run (reads whose first windows were too short), out[3] reserved */
+SQK_API int sqk_ctx_get_plan_counters_ex(sqk_ctx *ctx, int64_t out[4]);
 
 /* Kernels launched by this ctx since the last reset (every launch is counted where it is made). */
 SQK_API int sqk_ctx_get_launches(sqk_ctx *ctx, int64_t *out, int reset);

@@ -60,7 +60,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sqk_version", "sqk_last_error", "sqk_ctx_create", "sqk_ctx_destroy", "sqk_ctx_set_stream", "sqk_ctx_reset_stream", "sqk_ctx_sync",
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
-    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters",
+    "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters", "sqk_ctx_get_plan_counters_ex",
     "sqk_ctx_get_launches", "sqk_ctx_set_stats_generation", "sqk_device_alloc", "sqk_device_free", "sqk_ipc_export", "sqk_ipc_open",
     "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
 ]
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     L.sqk_ctx_set_chunk_samples.argtypes = [vp, i64]
     L.sqk_ctx_set_dtw_plan.argtypes = [vp, C.c_int]
     L.sqk_ctx_get_plan_counters.argtypes = [vp, C.POINTER(i64)]
+    L.sqk_ctx_get_plan_counters_ex.argtypes = [vp, C.POINTER(i64)]
     L.sqk_ctx_get_launches.argtypes = [vp, C.POINTER(i64), C.c_int]
     L.sqk_ctx_set_stats_generation.argtypes = [vp, C.c_int]
     L.sqk_device_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]

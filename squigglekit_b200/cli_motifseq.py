@@ -219,21 +219,31 @@ def flush(ctx, args, batch, model, m_order, L, out):
 def run_signal_file(ctx, args, model, m_order, L, out):
     """-s input through the batched text reader (squigglekit_b200.tsv): a batch of plain int16 lines goes from the parsed
     pinned buffer straight into one libsqk call and comes back as vectorised rows; a batch with anything else in it
-    (pA values, empty lines, all-zero reads) or -x takes the per-line path with the reference's messages."""
+    (pA values, empty lines, all-zero reads) or -x takes the per-line path with the reference's messages.
+    SQK_CLI_PROFILE=1 prints where the wall-clock time went (stderr)."""
+    import time
     from . import tsv
+    prof = os.environ.get("SQK_CLI_PROFILE")
+    tm = {"parse": 0.0, "heads": 0.0, "gpu": 0.0, "format": 0.0, "write": 0.0}
     models = [model[n] for n in m_order]
+    t_last = time.perf_counter()
     with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
         for b in rd:
+            t0 = time.perf_counter(); tm["parse"] += t0 - t_last
             if not b.status.any() and not args.sig_extract:
                 heads = [(h[0], h[1] if len(h) > 1 else "") for h in b.heads(2)]
+                t1 = time.perf_counter(); tm["heads"] += t1 - t0
                 hits, _ = ctx.motifseq(b.signals[:int(b.offsets[b.n])], b.offsets, models, scale=args.scale,
                                        scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision, want_kept=False)
+                t2 = time.perf_counter(); tm["gpu"] += t2 - t1
                 rows, skipped = format_rows(heads, m_order, hits, args.slope, args.intercept, args.std_const, L)
+                t3 = time.perf_counter(); tm["format"] += t3 - t2
                 for r, code in skipped:
                     why = "no samples left after outlier removal" if code == -1 else "MAD is 0: med-MAD scaling undefined"
                     sys.stderr.write("{} {}: {} - skipped\n".format(heads[r][0], heads[r][1], why))
                 if rows:
                     out.write("\n".join(rows) + "\n")
+                t_last = time.perf_counter(); tm["write"] += t_last - t3
                 continue
             batch = []
             for i in range(b.n):
@@ -255,6 +265,9 @@ def run_signal_file(ctx, args, model, m_order, L, out):
                     sig = vals
                 batch.append((h[0], h[1] if len(h) > 1 else "", sig))
             flush(ctx, args, batch, model, m_order, L, out)
+            t_last = time.perf_counter()
+    if prof:
+        sys.stderr.write("sqk profile (s): " + ", ".join("{} {:.3f}".format(k, v) for k, v in tm.items()) + "\n")
 
 
 def main(argv=None):

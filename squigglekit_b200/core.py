@@ -147,9 +147,9 @@ class Context:
 
     def plan_counters(self) -> dict:
         """Two-pass diagnostics of the most recent launch (first model): exact windows run, reads re-run in full."""
-        out = (C.c_int64 * 2)()
-        _cabi.check(self._lib.sqk_ctx_get_plan_counters(self._h, out))
-        return {"windows": int(out[0]), "fallback_reads": int(out[1])}
+        out = (C.c_int64 * 4)()
+        _cabi.check(self._lib.sqk_ctx_get_plan_counters_ex(self._h, out))
+        return {"windows": int(out[0]), "fallback_reads": int(out[1]), "second_attempt_windows": int(out[2])}
 
     def launches(self, reset: bool = True) -> int:
         """Kernels this context launched since the last reset (counted by the library at every launch site)."""

@@ -102,7 +102,7 @@ struct Slot {                 // everything one in-flight chunk needs
     cudaStream_t stream = nullptr;
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
-    DevBuf redo, mask, rm_p, rm_masks, bnd_a, bnd_b;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
+    DevBuf redo, mask, rm_p, rm_masks, bnd_a, bnd_b, jobs2, rtjobs, pending;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -689,7 +689,7 @@ static int check_motif_params(const sqk_motif_params *p)
     return SQK_OK;
 }
 
-#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head
+#define SQK_CTRS_PER_MODEL 8   // [0] read queue head, [1] #window jobs, [2] window queue head, [3] #fallback jobs, [4] fallback queue head, [5] #second-attempt jobs, [6] their queue head, [7] row-block queue head
 
 // A motif of more than 1024 points: its rows are cut into nb blocks of <= 1024; block b runs as one launch of the float64
 // kernel's row-block variant over a sub-batch of reads, reading row r0 - 1 of every column from the boundary buffer the
@@ -753,7 +753,7 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
             // per base): float64 row blocks, the last row of a block handed to the next one through a boundary row ---------
             cudaEvent_t eb;
             TRY(tick(c, SQK_K_DTW, st, &eb));
-            TRY(enqueue_long_motif(c, s, st, v, d_models + h_model_offsets[m], N, p, d_hits + m, n_models, ctr + 6));
+            TRY(enqueue_long_motif(c, s, st, v, d_models + h_model_offsets[m], N, p, d_hits + m, n_models, ctr + 7));
             if (publish && c->peers.n) {
                 PeerOut po{};
                 for (int q = 0; q < c->peers.n; q++) po.peer[po.n++] = c->peers.peer[q] + c->peer_base * n_models + m;
@@ -798,6 +798,9 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         TRY(ensure(s.fbjobs, (size_t)v.n_reads * sizeof(DtwJob)));
         TRY(ensure(s.lbreads, (size_t)v.n_reads * sizeof(LbRead)));
         TRY(ensure(s.jobres, (size_t)v.n_reads * SQK_LB_MAX_CLUSTERS * sizeof(sqk_hit)));
+        TRY(ensure(s.jobs2, (size_t)v.n_reads * SQK_LB_MAX_CLUSTERS * sizeof(DtwJob)));
+        TRY(ensure(s.rtjobs, (size_t)v.n_reads * SQK_LB_MAX_CLUSTERS * sizeof(DtwJob)));
+        TRY(ensure(s.pending, (size_t)v.n_reads));
         double xmax = 0.0;
         for (int i = h_model_offsets[m]; i < h_model_offsets[m + 1]; i++) xmax = std::max(xmax, std::fabs(h_models[i]));
         if (!(xmax < 1e30)) return fail(SQK_ERR_ARG, "model %d holds a non-finite point", m);
@@ -811,7 +814,10 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         b.reads = (LbRead *)s.lbreads.p;
         b.xmax_abs = xmax;
         b.W = sqk_lb_window(N);
-        if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the fallback
+        b.W2 = sqk_lb_window_retry(N);
+        if (const char *e = getenv("SQK_LB_WINDOW")) { const int wv = atoi(e); if (wv > 0) b.W = wv; }   // test knob: small windows force the second attempt / fallback
+        if (const char *e = getenv("SQK_LB_WINDOW2")) { const int wv = atoi(e); b.W2 = wv > 0 ? wv : 0; } // test knob: 0 = no second attempt
+        b.jobs2 = b.W2 > 0 ? (DtwJob *)s.jobs2.p : nullptr;
         b.short_len = 2 * (b.W + N);
         { static int env_cols = -1; if (env_cols < 0) { const char *ec = getenv("SQK_LB_COLS"); env_cols = ec ? atoi(ec) : 0; } b.cols = (env_cols == 2 || env_cols == 4) ? env_cols : 0; }   // experiments
         TRY(tick(c, SQK_K_DTW_LB, st, &eb));
@@ -825,26 +831,38 @@ static int enqueue_motifseq(sqk_ctx *c, Slot &s, cudaStream_t st, const View &v,
         a.job_out = (sqk_hit *)s.jobres.p; a.job_out_stride = 1;
         e = fn(K, a, c->n_sms, st);
         if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW window launch (N=%d, K=%d, L=%d): %s", N, K, L, cudaGetErrorString(e));
+        // wide-lane launcher for the (few) second-attempt and full-length jobs: they run at the latency of one job, so each
+        // gets as many lanes as the motif allows (N = 80: 3 rows on 32 lanes instead of 10 on 8 -- same bits, a third of the time)
+        int FL = L, FK = K;
+        sqk_dtw_launcher ffn = fn;
+        if (!c->force_lanes) pick_dtw_wide(N, &FL, &FK, &ffn);
         FinalizeArgs f{};
         f.reads = b.reads; f.jobres = (const sqk_hit *)s.jobres.p; f.n_reads = (int)v.n_reads;
         f.hits = a.hits; f.hit_stride = a.hit_stride;
         f.base = v.base; f.offsets = v.offsets; f.read0 = v.read0; f.stats = a.stats;
         f.fb_jobs = (DtwJob *)s.fbjobs.p; f.n_fb = ctr + 3;
+        f.stage = 1; f.jobs2 = b.jobs2; f.rt_jobs = (DtwJob *)s.rtjobs.p; f.n_rt = ctr + 5; f.pending = (unsigned char *)s.pending.p;
         f.po = po;
-        sqk_dtw_finalize_kernel<<<(unsigned)((v.n_reads + 255) / 256), 256, 0, st>>>(f);
+        const unsigned fgrid = (unsigned)((v.n_reads + 255) / 256);
+        sqk_dtw_finalize_kernel<<<fgrid, 256, 0, st>>>(f);
         CU(cudaGetLastError());
+        if (b.jobs2) {
+            // second attempt: the reads whose windows tainted, behind windows of W2 columns; then decide again
+            a.counter = ctr + 6;
+            a.jobs = f.rt_jobs; a.n_jobs = ctr + 5;
+            a.job_out = (sqk_hit *)s.jobres.p; a.job_out_stride = 1;
+            e = ffn(FK, a, c->n_sms, st);
+            if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW second-attempt launch (N=%d, K=%d, L=%d): %s", N, FK, FL, cudaGetErrorString(e));
+            f.stage = 2;
+            sqk_dtw_finalize_kernel<<<fgrid, 256, 0, st>>>(f);
+            CU(cudaGetLastError());
+            c->n_launches += 2;
+        }
         a.counter = ctr + 4;
         a.jobs = f.fb_jobs; a.n_jobs = ctr + 3;
         a.job_out = a.hits; a.job_out_stride = a.hit_stride;
-        // The (few) full-length jobs run at the latency of one read: give each as many lanes as the motif allows, so that a
-        // lane has few rows per column step (N = 80: 3 rows on 32 lanes instead of 10 on 8 -- same bits, a third of the time).
-        {
-            int FL = L, FK = K;
-            sqk_dtw_launcher ffn = fn;
-            if (!c->force_lanes) pick_dtw_wide(N, &FL, &FK, &ffn);
-            e = ffn(FK, a, c->n_sms, st);
-            if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, FK, FL, cudaGetErrorString(e));
-        }
+        e = ffn(FK, a, c->n_sms, st);
+        if (e != cudaSuccess) return fail(SQK_ERR_CUDA, "DTW fallback launch (N=%d, K=%d, L=%d): %s", N, FK, FL, cudaGetErrorString(e));
         c->n_launches += 4;                      // lower-bound scan, windows, finalize, fallback
         if (po.n) {                              // the (few) reads the fallback just wrote
             sqk_publish_kernel<<<8, 256, 0, st>>>(a.hits, a.hit_stride, f.fb_jobs, ctr + 3, (int)v.n_reads, po);
@@ -1199,7 +1217,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
     for (int i = 0; i < 2; i++) {
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
-        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks); release(s.bnd_a); release(s.bnd_b);
+        release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks); release(s.bnd_a); release(s.bnd_b); release(s.jobs2); release(s.rtjobs); release(s.pending);
         release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres); release(s.redo); release(s.mask);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -1304,6 +1322,20 @@ int sqk_ctx_get_plan_counters(sqk_ctx *c, int64_t out[2])
     unsigned h[SQK_CTRS_PER_MODEL];
     CU(cudaMemcpy(h, c->slot[0].counter.p, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = h[1]; out[1] = h[3];
+    return SQK_OK;
+}
+
+int sqk_ctx_get_plan_counters_ex(sqk_ctx *c, int64_t out[4])
+{
+    if (!c || !out) return fail(SQK_ERR_ARG, "NULL argument");
+    Guard g(c->device);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!c->slot[0].counter.p) return SQK_OK;
+    CU(cudaStreamSynchronize(device_stream(c)));
+    CU(cudaStreamSynchronize(c->slot[0].stream));
+    unsigned h[SQK_CTRS_PER_MODEL];
+    CU(cudaMemcpy(h, c->slot[0].counter.p, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[1]; out[1] = h[3]; out[2] = h[5];
     return SQK_OK;
 }
 

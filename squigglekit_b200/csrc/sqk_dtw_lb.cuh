@@ -41,6 +41,8 @@ struct LbArgs {
     LbRead *reads;            // [n_reads]
     double xmax_abs;          // max |motif point|
     int W;                    // window columns in front of a cluster
+    int W2;                   // ... of the second attempt (0: none)
+    DtwJob *jobs2;            // [n_reads * SQK_LB_MAX_CLUSTERS]: the second-attempt job of cluster q of read r at r * MAX + q
     int short_len;            // reads with n_kept <= short_len skip pass 1 (one full-length job)
     int cols;                 // signal columns per wavefront step: 2, 4, or 0 = the launcher's rule
 };
@@ -71,17 +73,34 @@ struct LbWatch {
 };
 
 __device__ __forceinline__ void lb_candidate(float u, int j, LbWatch &wt, LbClusters *cl, const int32_t *ck, int n_ref,
-                                             int64_t cursor0, int ch, int W)
+                                             int64_t cursor0, int ch, int W, int W2 = 0)
 {
     if (u <= wt.thr_u && (unsigned)j < (unsigned)wt.n) {   // (stale ring entries past the end of the read never count)
         const float lj = sqk_lb_adjust(u, j, wt.N, wt.w);
         if (lj <= wt.thr) {
-            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = ch; sc.W = W;
+            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = cursor0; sc.ch = ch; sc.W = W; sc.W2 = W2;
             lbc_event(*cl, j, lj, wt.runmin, wt.thr, wt.aeps, wt.bslack, sc);
             // the threshold may have moved: keep the cheap test valid for the rest of this block and the next
             wt.thr_u = sqk_lb_thr_u(wt.thr, sqk_mul_ru((float)(j + wt.N + 2 * ch), wt.w));
         }
     }
+}
+
+// The rare path of the scan, OUT OF LINE: up to eight last-row values of consecutive columns from j0 on, in column order.
+// Everything travels by value (the watch state comes back in a small struct), so that the hot loop's register allocation
+// knows nothing of the cluster bookkeeping behind this call.
+struct LbWatchUpd { float runmin, thr, thr_u; };
+struct LbVals8 { float v[8]; };
+static __device__ __noinline__ LbWatchUpd lb_candidates(LbVals8 vals, int count, int j0, float runmin, float thr, float thr_u, float aeps,
+                                                 float bslack, float w, int n, int N, LbClusters *cl, const int32_t *ck, int n_ref,
+                                                 int64_t cursor0, int ch, int W, int W2)
+{
+    LbWatch wt;
+    wt.runmin = runmin; wt.thr = thr; wt.thr_u = thr_u; wt.aeps = aeps; wt.bslack = bslack; wt.w = w; wt.wstep = 0.0f; wt.n = n; wt.N = N;
+#pragma unroll 1
+    for (int q = 0; q < count; q++) lb_candidate(vals.v[q], j0 + q, wt, cl, ck, n_ref, cursor0, ch, W, W2);
+    LbWatchUpd r; r.runmin = wt.runmin; r.thr = wt.thr; r.thr_u = wt.thr_u;
+    return r;
 }
 
 // One wavefront step of one lane: column (t - l) of the U recurrence for this lane's K rows (sqk_dtw_plan.cuh).
@@ -401,15 +420,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                 lb_step4<K, L, RAGGED>(c2, c, x, raddr, l, pass0, tf, bot4, prev_up, wt);
                 // one test per eight columns of the last row (rare: a column that may be a candidate); in column order
                 if (fminf(fminf(fminf(a1, b1), fminf(c1, d1)), fminf(fminf(bot4[0], bot4[1]), fminf(bot4[2], bot4[3]))) <= wt.thr_u) {
-                    const int j = t - 4 * (L - 1);
-                    lb_candidate(a1, j, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(b1, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(c1, j + 2, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(d1, j + 3, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot4[0], j + 4, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot4[1], j + 5, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot4[2], j + 6, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot4[3], j + 7, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    LbVals8 vals;
+                    vals.v[0] = a1; vals.v[1] = b1; vals.v[2] = c1; vals.v[3] = d1;
+                    vals.v[4] = bot4[0]; vals.v[5] = bot4[1]; vals.v[6] = bot4[2]; vals.v[7] = bot4[3];
+                    const LbWatchUpd up = lb_candidates(vals, 8, t - 4 * (L - 1), wt.runmin, wt.thr, wt.thr_u, wt.aeps, wt.bslack, wt.w,
+                                                        wt.n, wt.N, cl, ck, n_ref, cursor0, 8 * L, a.W, a.W2);
+                    wt.runmin = up.runmin; wt.thr = up.thr; wt.thr_u = up.thr_u;
                 }
                 t += 8;
             }
@@ -421,11 +437,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                 lb_step2<K, L, RAGGED>(c2, c, x, raddr, l, pass0, t + 2, tf, bot, bot_b, prev_up, wt, cl, ck, n_ref, cursor0, a.W);
                 // one test per four columns of the last row (rare: a column that may be a candidate); in column order
                 if (fminf(fminf(a1, b1), fminf(bot, bot_b)) <= wt.thr_u) {
-                    const int j = t - 2 * (L - 1);
-                    lb_candidate(a1, j, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(b1, j + 1, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot, j + 2, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
-                    lb_candidate(bot_b, j + 3, wt, cl, ck, n_ref, cursor0, 8 * L, a.W);
+                    LbVals8 vals;
+                    vals.v[0] = a1; vals.v[1] = b1; vals.v[2] = bot; vals.v[3] = bot_b;
+                    vals.v[4] = 0.0f; vals.v[5] = 0.0f; vals.v[6] = 0.0f; vals.v[7] = 0.0f;
+                    const LbWatchUpd up = lb_candidates(vals, 4, t - 2 * (L - 1), wt.runmin, wt.thr, wt.thr_u, wt.aeps, wt.bslack, wt.w,
+                                                        wt.n, wt.N, cl, ck, n_ref, cursor0, 8 * L, a.W, a.W2);
+                    wt.runmin = up.runmin; wt.thr = up.thr; wt.thr_u = up.thr_u;
                 }
                 t += 4;
             }
@@ -455,6 +472,12 @@ __global__ void __launch_bounds__(SQK_LB_THREADS, SQK_LB_MINB(K)) sqk_dtw_lb_ker
                         jb.cursor = cl->cursor[q]; jb.read = my_read; jb.col0 = cl->col0[q]; jb.n_cols = cl->hi[q] - cl->col0[q] + 1;
                         jb.arg_lo = cl->lo[q] - cl->col0[q]; jb.tainted = cl->tainted[q]; jb.out = my_read * SQK_LB_MAX_CLUSTERS + q;
                         a.jobs[at + q] = jb;
+                        if (a.jobs2) {                         // the same cluster behind a wider window, should the first one taint
+                            DtwJob j2 = jb;
+                            j2.cursor = cl->cursor2[q]; j2.col0 = cl->col02[q]; j2.n_cols = cl->hi[q] - cl->col02[q] + 1;
+                            j2.arg_lo = cl->lo[q] - cl->col02[q]; j2.tainted = cl->tainted2[q];      // -1: no second attempt
+                            a.jobs2[my_read * SQK_LB_MAX_CLUSTERS + q] = j2;
+                        }
                     }
                     rec.n_jobs = nj;
                 }
@@ -491,7 +514,12 @@ struct FinalizeArgs {
     sqk_hit *hits; int hit_stride;
     const int16_t *base; const int64_t *offsets; int64_t read0;
     const ReadStats *stats;
-    DtwJob *fb_jobs; unsigned int *n_fb;
+    DtwJob *fb_jobs; unsigned int *n_fb;       // full-length jobs
+    // second attempt (stage 1 fills, stage 2 reads `pending`)
+    int stage;                                 // 1: after the first windows; 2: after the second-attempt windows
+    const DtwJob *jobs2;                       // [n_reads][SQK_LB_MAX_CLUSTERS] or null: no second attempt
+    DtwJob *rt_jobs; unsigned int *n_rt;       // second-attempt job list
+    unsigned char *pending;                    // [n_reads]: 1 = waiting for its second attempt
     PeerOut po;
 };
 
@@ -499,6 +527,9 @@ static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_reads) return;
+    if (a.stage == 2) {
+        if (!a.pending[r]) return;                     // settled in stage 1
+    } else if (a.pending) a.pending[r] = 0;
     const LbRead rec = a.reads[r];
     if (rec.n_jobs < 0) {                              // status hit already written by pass 1: only forward it
         if (a.po.n) sqk_publish(a.po, (int64_t)r * a.hit_stride, a.hits[(int64_t)r * a.hit_stride]);
@@ -510,16 +541,28 @@ static __global__ void sqk_dtw_finalize_kernel(const FinalizeArgs a)
         const sqk_hit h = a.jobres[(int64_t)r * SQK_LB_MAX_CLUSTERS + q];
         res[q].start = h.start; res[q].end = h.end; res[q].dist = h.dist;
     }
-    if (sqk_lb_decide(rec, res, &best)) {
+    bool only_taint = false;
+    if (sqk_lb_decide(rec, res, &best, &only_taint)) {
         sqk_hit h; h.start = best.start; h.end = best.end; h.dist = best.dist;
         a.hits[(int64_t)r * a.hit_stride] = h;
         sqk_publish(a.po, (int64_t)r * a.hit_stride, h);
-    } else {
-        DtwJob jb;
-        jb.cursor = aligned_block_start(a.base, a.offsets[a.read0 + r]);
-        jb.read = r; jb.col0 = 0; jb.n_cols = a.stats[r].n_kept; jb.arg_lo = 0; jb.tainted = 0; jb.out = r;
-        a.fb_jobs[atomicAdd(a.n_fb, 1u)] = jb;
+        return;
     }
+    if (a.stage == 1 && only_taint && a.jobs2) {
+        // a window was too short: the same clusters behind wider windows, if every one of them can be located
+        bool ok = true;
+        for (int q = 0; q < nj; q++) ok = ok && a.jobs2[(int64_t)r * SQK_LB_MAX_CLUSTERS + q].tainted >= 0;
+        if (ok) {
+            const unsigned at = atomicAdd(a.n_rt, (unsigned)nj);
+            for (int q = 0; q < nj; q++) a.rt_jobs[at + q] = a.jobs2[(int64_t)r * SQK_LB_MAX_CLUSTERS + q];
+            a.pending[r] = 1;
+            return;
+        }
+    }
+    DtwJob jb;
+    jb.cursor = aligned_block_start(a.base, a.offsets[a.read0 + r]);
+    jb.read = r; jb.col0 = 0; jb.n_cols = a.stats[r].n_kept; jb.arg_lo = 0; jb.tainted = 0; jb.out = r;
+    a.fb_jobs[atomicAdd(a.n_fb, 1u)] = jb;
 }
 
 // Publication of records that other kernels wrote into the local array: the reads of a job list (the full-length

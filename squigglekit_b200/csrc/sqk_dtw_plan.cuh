@@ -76,6 +76,9 @@ struct LbClusters {
     // where each cluster's window starts (found when the cluster opens; tainted == -1: not locatable)
     int32_t col0[SQK_LB_MAX_CLUSTERS], tainted[SQK_LB_MAX_CLUSTERS];
     int64_t cursor[SQK_LB_MAX_CLUSTERS];
+    // ... and where the wider window of the second attempt starts (W2 columns in front; tainted2 == -1: not locatable)
+    int32_t col02[SQK_LB_MAX_CLUSTERS], tainted2[SQK_LB_MAX_CLUSTERS];
+    int64_t cursor2[SQK_LB_MAX_CLUSTERS];
 };
 
 // ---- float32 helpers with a stated rounding direction (device: one instruction; host: emulated) ----------
@@ -187,22 +190,31 @@ SQK_HD float sqk_lb_thr_u(float thr, float offmax)
 
 // Columns in front of a cluster's first candidate.  Alignments of an N-point motif span <= 1.43 N columns on the
 // synthetic benchmark reads and <= 1.40 N on the 60 reads of the reference's example_fast5s.tar (163-point example
-// model).  A window that turns out too short taints the minimum and the read is re-run in full -- and a full-length
-// re-run costs the latency of one whole read (~0.6 ms at 4096 samples) however few reads need it: W = 1.5 N + 32 was
-// measured 0.6 ms per 100 k reads SLOWER than 2 N + 32 because 2 of the 100 k reads fell back.  So W is generous.
-SQK_HD int sqk_lb_window(int N) { return 2 * N + 32; }
+// model).  A window that turns out too short taints the minimum; the read then gets a SECOND ATTEMPT with windows of
+// W2 = 4 (2N + 32) columns (run on 32 lanes per read: a few hundred columns at the latency of a few hundred short steps),
+// and only if that fails, too, the full-length re-run -- which costs the latency of one whole read however few reads need
+// it.  With the second attempt a taint is cheap, so W is 1.33 N + 16 (CPU replay on 800 benchmark reads, columns per read
+// including second attempts: 197 at 1.5 N + 32, 167 at 1.3 N + 16 with one read in 800 needing the second attempt, 149 at
+// 1.1 N + 8 with nine; round 1, without a second attempt: 2 N + 32 = 235, because two full-length re-runs per 100 k reads
+// cost more than the longer windows).
+SQK_HD int sqk_lb_window(int N) { return N + N / 3 + 16; }
+SQK_HD int sqk_lb_window_retry(int N) { return 4 * (2 * N + 32); }
 
 // Where does the window of a cluster starting at column `lo` begin?  ck[(k) % SQK_LB_CKPT] = number of kept
 // samples in front of refill k (refills fetch `ch` raw samples each, the first at cursor0); n_ref refills have
 // happened.  Asked when the cluster opens, i.e. while its neighbourhood is still in the ring.  Returns false
 // when the boundary column is no longer in the ring (-> fallback).
 SQK_HD bool sqk_lb_window_start(const int32_t *ck, int n_ref, int64_t cursor0, int ch, int lo, int W,
-                                int64_t *cursor, int32_t *col0, int32_t *tainted)
+                                int64_t *cursor, int32_t *col0, int32_t *tainted, int k_from = -1)
 {
     const int target = lo - W - 1;                // boundary column
     if (target <= 0) { *cursor = cursor0; *col0 = 0; *tainted = 0; return true; }
     const int oldest = n_ref > SQK_LB_CKPT ? n_ref - SQK_LB_CKPT : 0;
-    for (int k = n_ref - 1; k >= oldest; k--) {
+    // any refill whose kept-sample count is <= target will do (an earlier one only makes the window longer); the search
+    // walks back from the newest one, or from k_from when the caller knows a later start is pointless
+    int k = n_ref - 1;
+    if (k_from >= 0 && k_from < k) k = k_from;
+    for (; k >= oldest; k--) {
         const int c0 = ck[k % SQK_LB_CKPT];
         if (c0 <= target) {
             if (k == 0) { *cursor = cursor0; *col0 = 0; *tainted = 0; return true; }
@@ -220,6 +232,7 @@ struct LbScan {
     int64_t cursor0;
     int ch;
     int W;
+    int W2;     // window of the second attempt (0: none)
 };
 
 SQK_HD void lbc_reset(LbClusters &c) { c.n = 0; c.overflow = 0; }
@@ -239,6 +252,7 @@ SQK_HD void lbc_event(LbClusters &c, int j, float v, float &runmin, float &thr, 
             if (k != i) {
                 c.lo[k] = c.lo[i]; c.hi[k] = c.hi[i]; c.mn[k] = c.mn[i];
                 c.cursor[k] = c.cursor[i]; c.col0[k] = c.col0[i]; c.tainted[k] = c.tainted[i];
+                c.cursor2[k] = c.cursor2[i]; c.col02[k] = c.col02[i]; c.tainted2[k] = c.tainted2[i];
             }
             k++;
         }
@@ -248,6 +262,14 @@ SQK_HD void lbc_event(LbClusters &c, int j, float v, float &runmin, float &thr, 
     c.lo[c.n] = j; c.hi[c.n] = j; c.mn[c.n] = v;
     if (!sqk_lb_window_start(sc.ck, sc.n_ref, sc.cursor0, sc.ch, j, sc.W, &c.cursor[c.n], &c.col0[c.n], &c.tainted[c.n]))
         c.tainted[c.n] = -1;                      // window start unknown: the read falls back if this cluster survives
+    c.tainted2[c.n] = -1; c.col02[c.n] = 0; c.cursor2[c.n] = 0;
+    if (sc.W2 > 0) {
+        // every refill holds at most ch kept samples: W2 columns back is at least W2 / ch refills back -- start the walk there
+        const int back = sc.W2 / sc.ch;
+        const int from = sc.n_ref - 1 - back > 0 ? sc.n_ref - 1 - back : 0;
+        if (!sqk_lb_window_start(sc.ck, sc.n_ref, sc.cursor0, sc.ch, j, sc.W2, &c.cursor2[c.n], &c.col02[c.n], &c.tainted2[c.n], from))
+            c.tainted2[c.n] = -1;                 // no second attempt for this read
+    }
     c.n++;
 }
 
@@ -260,6 +282,7 @@ SQK_HD void lbc_finish(LbClusters &c, float thr)
             if (k != i) {
                 c.lo[k] = c.lo[i]; c.hi[k] = c.hi[i]; c.mn[k] = c.mn[i];
                 c.cursor[k] = c.cursor[i]; c.col0[k] = c.col0[i]; c.tainted[k] = c.tainted[i];
+                c.cursor2[k] = c.cursor2[i]; c.col02[k] = c.col02[i]; c.tainted2[k] = c.tainted2[i];
             }
             k++;
         }
@@ -270,8 +293,9 @@ SQK_HD void lbc_finish(LbClusters &c, float thr)
 // Combine the exact window results of one read (sqk_hit layout: start, end, dist).  Returns true when `best`
 // is proven to be mlpy's result, false when the read must be re-run over its full length.
 struct SqkHitLite { int32_t start, end; double dist; };
-SQK_HD bool sqk_lb_decide(const LbRead &r, const SqkHitLite *res, SqkHitLite *best)
+SQK_HD bool sqk_lb_decide(const LbRead &r, const SqkHitLite *res, SqkHitLite *best, bool *only_taint = nullptr)
 {
+    if (only_taint) *only_taint = false;
     if (r.flags != 0 || r.n_jobs <= 0) return false;
     SqkHitLite b = res[0];
     bool taint = (res[0].start == SQK_TAINT);
@@ -279,7 +303,10 @@ SQK_HD bool sqk_lb_decide(const LbRead &r, const SqkHitLite *res, SqkHitLite *be
         if (res[i].start == SQK_TAINT) taint = true;
         if (res[i].dist < b.dist) b = res[i];     // clusters are in column order: strict < keeps the first minimum
     }
-    if (taint) return false;
+    if (taint) {                                  // a window was too short: wider windows can settle it
+        if (only_taint) *only_taint = true;
+        return false;
+    }
     if (!(b.dist <= (double)r.thr)) return false; // also rejects NaN
     *best = b;
     return true;

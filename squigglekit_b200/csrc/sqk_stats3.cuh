@@ -164,6 +164,7 @@ __device__ __noinline__ void s3_compact_all(unsigned bufs, int h0, int len, int 
         const int v = p < len ? s2_lds_s16(bufs + 2u * (unsigned)(h0 + p)) : 0;
         const bool keep = p < len && (unsigned)(v - wlo) <= span;
         const unsigned m = __ballot_sync(SQK_FULL_MASK, keep);
+        __syncwarp();                                           // every lane's load before any lane's store
         if (keep) s3_sts_u16(bufs + 2u * (unsigned)(h0 + wpos + __popc(m & ((1u << lane) - 1u))), v);
         wpos += __popc(m);
         __syncwarp();

@@ -58,9 +58,10 @@ extern "C" {
 // y: normalised kept samples (float64) of one read, sv: the same samples before normalisation, n of them; keep[raw_len]: 1 where the raw sample survived the
 // outlier filter (sum == n); align_off: raw samples between the aligned block start and the read's first sample;
 // ch: raw samples per refill (8 * lanes).  out: start, end; *dist.  diag[0..7]: n_clusters, n_jobs, fallback
-// (0 proven, 1 fallback), flags, lower-bound violations (must be 0), tainted windows, window columns, max L gap *1e9.
+// (0 proven, 1 fallback), flags, lower-bound violations (must be 0), tainted windows, window columns, max L gap *1e9;
+// diag[8]: 1 if the read needed the second attempt.  W2_in < 0: the default second-attempt window, 0: none.
 int plan_two_pass(const double *x, int N, const double *y, const double *sv, int n, const uint8_t *keep, int raw_len, int align_off, int ch,
-                  int lo, int hi, double center, double scale, int W, int32_t *out, double *dist, int64_t *diag)
+                  int lo, int hi, double center, double scale, int W, int W2_in, int32_t *out, double *dist, int64_t *diag)
 {
     const float inf = std::numeric_limits<float>::infinity();
     double xmax = 0.0;
@@ -69,6 +70,7 @@ int plan_two_pass(const double *x, int N, const double *y, const double *sv, int
     float aeps, bslack;
     sqk_lb_slack(N, w, &aeps, &bslack);
     if (W <= 0) W = sqk_lb_window(N);
+    const int W2 = W2_in < 0 ? sqk_lb_window_retry(N) : W2_in;       // 0: no second attempt
 
     // exact last row of the whole read: the property under test is L[j] <= C[N-1][j]
     std::vector<double> crow(n);
@@ -83,9 +85,11 @@ int plan_two_pass(const double *x, int N, const double *y, const double *sv, int
     int n_ref = 0, wcount = 0, raw = -align_off;       // raw: position of the next refill relative to the read's first sample
     int64_t violations = 0; double max_gap = 0.0;
     // the kernel's schedule: blocks of S columns between refills, the last lane LAG columns behind lane 0
-    const int lanes = ch / 8, cols = SQK_LB_COLS, LAG = cols * (lanes - 1);
-    const int S = lanes == 1 ? 8 : (cols == 2 ? 6 * lanes : 7 * lanes);
-    float thr_u = -inf, prev_virt = 0.0f;
+    // (four columns per step when a lane holds <= 12 rows on >= 4 lanes, as sqk_dtw_lb_launch.cuh decides; two otherwise)
+    const int lanes = ch / 8, rows = (N + lanes - 1) / lanes, cols = (lanes >= 4 && rows <= 12) ? 4 : 2, LAG = cols * (lanes - 1);
+    const int S = lanes == 1 ? 8 : (cols == 4 ? 12 * lanes : 6 * lanes);
+    const float wstep = sqk_mul_rd((float)cols, w);
+    float thr_u = -inf, prev_virt = 0.0f, step_virt = 0.0f;
     int64_t missed = 0;
     for (int j = 0; j < n; j++) {
         // the kernel refills ahead of use (whenever fewer than S columns are buffered beyond the wavefront)
@@ -98,8 +102,11 @@ int plan_two_pass(const double *x, int N, const double *y, const double *sv, int
         const int t = j - j % cols + LAG;
         if (j == 0 || (t % S == 0 && j % cols == 0)) thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(t - t % S + S + N), w));
         const float y32 = sqk_lb_y32(sv[j], center, sqk_lb_inv_scale(scale));
-        // free-start row: exact-ish at the first column of each block (lane 0's clock is the column), += w inside
-        const float virt = (j % S == 0) ? sqk_lb_virtual((float)j, w) : sqk_lb_virtual_next(prev_virt, w);
+        // free-start row: exact-ish at the first column of each block (lane 0's clock is the column); inside a block one
+        // rounded-down add of cols * w per step, every column of a step taking the value of the step's first column
+        if (j % S == 0) step_virt = sqk_lb_virtual((float)j, w);
+        else if (j % cols == 0) step_virt = sqk_add_rd(step_virt, wstep);
+        const float virt = step_virt;
         for (int i = 0; i < N; i++) {
             float m;
             if (i == 0) m = std::fmin(std::fmin(virt, prev_virt), j == 0 ? inf : c[0]);   // free-start row: j*w, (j-1)*w, left
@@ -117,7 +124,7 @@ int plan_two_pass(const double *x, int N, const double *y, const double *sv, int
         if (crow[j] - (double)v > max_gap && crow[j] <= truth.dist + 1.0) max_gap = crow[j] - (double)v;
         if (v <= thr && !(u <= thr_u)) missed++;      // the cheap test must never miss a candidate
         if (u <= thr_u && v <= thr) {
-            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = -(int64_t)align_off; sc.ch = ch; sc.W = W;
+            LbScan sc; sc.ck = ck; sc.n_ref = n_ref; sc.cursor0 = -(int64_t)align_off; sc.ch = ch; sc.W = W; sc.W2 = W2;
             lbc_event(cl, j, v, runmin, thr, aeps, bslack, sc);
             thr_u = sqk_lb_thr_u(thr, sqk_mul_ru((float)(j + N + 2 * ch), w));
         }
@@ -144,13 +151,33 @@ int plan_two_pass(const double *x, int N, const double *y, const double *sv, int
         if (h.start == SQK_TAINT) tainted_windows++;
         window_cols += n_cols;
     }
-    const bool proven = sqk_lb_decide(rec, res, &best);
+    bool only_taint = false;
+    bool proven = sqk_lb_decide(rec, res, &best, &only_taint);
+    int64_t second_attempt = 0;
+    if (!proven && only_taint && W2 > 0) {
+        // second attempt (sqk_dtw_finalize_kernel, stage 1 -> 2): the same clusters behind windows of W2 columns
+        bool ok = true;
+        for (int q = 0; q < rec.n_jobs; q++) ok = ok && cl.tainted2[q] >= 0;
+        if (ok) {
+            second_attempt = 1;
+            for (int q = 0; q < rec.n_jobs; q++) {
+                int kept_before = 0;
+                for (int r = 0; r < cl.cursor2[q] && r < raw_len; r++) kept_before += keep[r];
+                if (kept_before != cl.col02[q]) return -200 - q;            // checkpoint bookkeeping broken
+                const int n_cols = cl.hi[q] - cl.col02[q] + 1;
+                const Hit h = exact_window(x, N, y, cl.col02[q], n_cols, cl.lo[q] - cl.col02[q], cl.tainted2[q] != 0);
+                res[q].start = h.start; res[q].end = h.end; res[q].dist = h.dist;
+                window_cols += n_cols;
+            }
+            proven = sqk_lb_decide(rec, res, &best);
+        }
+    }
     Hit fin;
     if (proven) { fin.start = best.start; fin.end = best.end; fin.dist = best.dist; }
     else fin = truth;                                                    // the kernel re-runs the full read
     out[0] = fin.start; out[1] = fin.end; *dist = fin.dist;
     diag[0] = cl.n; diag[1] = rec.n_jobs; diag[2] = proven ? 0 : 1; diag[3] = rec.flags; diag[4] = violations;
-    diag[5] = tainted_windows; diag[6] = window_cols; diag[7] = (int64_t)(max_gap * 1e9);
+    diag[5] = tainted_windows; diag[6] = window_cols; diag[7] = (int64_t)(max_gap * 1e9); diag[8] = second_attempt;
     // a proven result must equal the full exact recurrence
     if (proven && (fin.start != truth.start || fin.end != truth.end || fin.dist != truth.dist)) return -1;
     return 0;

@@ -42,9 +42,10 @@ def test_native_arm_line():
     assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["scaling"] == "weak" and d["vs_baseline"] is None
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    # default plan on 4096-sample reads: stats (+ its redo list) + lower-bound scan + (windows, finalize, fallback) per step
+    # default plan on 4096-sample reads: stats (+ its redo list) + lower-bound scan + windows, finalize, second-attempt windows,
+    # finalize, full-length fallback per step
     assert d["plan"]["name"] == "two_pass" and r["kernel"] == "sqk_dtw_lb_kernel"
-    assert r["kernel_ms_per_launch"] > 0 and d["gpu_launches"] == 6 * d["steps"]
+    assert r["kernel_ms_per_launch"] > 0 and d["gpu_launches"] == 8 * d["steps"]
     assert d["plan"]["full_length_fallback_reads_per_step"] <= 0.01 * 20000
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 20000 * 4096 * 2 + 20001 * 8
     assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] > 0

@@ -110,17 +110,37 @@ def test_two_pass_tie_heavy_integer_reads(planned):
     check(planned, sig, off, synth.make_motif(), "zscale", what="ties/zscale")
 
 
-def test_two_pass_small_window_falls_back(planned):
-    """A window far too small for the alignment taints the minimum: every such read must be re-run in full."""
+def test_two_pass_small_window_second_attempt_and_fallback(planned):
+    """A window far too small for the alignment taints the minimum.  With the second attempt (windows of W2 columns) nearly
+    every such read is settled there; without it (W2 = 0), or with a second window that is too small as well, every such
+    read must be re-run in full.  Same bits every way."""
     import torch
     planned.set_dtw_plan("two_pass")
-    os.environ["SQK_LB_WINDOW"] = "12"
     motif = synth.make_motif()
     sig, off, _ = synth.motifseq_reads_np(256, 4096, motif)
-    check(planned, sig, off, motif, "zscale", what="window=12")
-    planned.motifseq(torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda(), motif, scale="zscale", max_read_len=4096)
-    torch.cuda.synchronize()
-    assert planned.plan_counters()["fallback_reads"] >= 128
+    dsig, doff = torch.from_numpy(sig).cuda(), torch.from_numpy(off).cuda()
+    try:
+        os.environ["SQK_LB_WINDOW"] = "12"
+        check(planned, sig, off, motif, "zscale", what="window=12, default second attempt")
+        planned.motifseq(dsig, doff, motif, scale="zscale", max_read_len=4096)
+        torch.cuda.synchronize()
+        pc = planned.plan_counters()
+        assert pc["second_attempt_windows"] >= 128 and pc["fallback_reads"] <= 8, pc
+        os.environ["SQK_LB_WINDOW2"] = "0"
+        check(planned, sig, off, motif, "zscale", what="window=12, no second attempt")
+        planned.motifseq(dsig, doff, motif, scale="zscale", max_read_len=4096)
+        torch.cuda.synchronize()
+        pc = planned.plan_counters()
+        assert pc["second_attempt_windows"] == 0 and pc["fallback_reads"] >= 128, pc
+        os.environ["SQK_LB_WINDOW2"] = "20"
+        check(planned, sig, off, motif, "zscale", what="window=12, second attempt of 20 columns")
+        planned.motifseq(dsig, doff, motif, scale="zscale", max_read_len=4096)
+        torch.cuda.synchronize()
+        pc = planned.plan_counters()
+        assert pc["second_attempt_windows"] >= 128 and pc["fallback_reads"] >= 100, pc
+    finally:
+        os.environ.pop("SQK_LB_WINDOW", None)
+        os.environ.pop("SQK_LB_WINDOW2", None)
 
 
 def test_two_pass_multiple_models_and_outlier_windows(planned):
