@@ -254,6 +254,14 @@ SQK_API int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int s
  * needed when cap is too small / out is NULL) */
 SQK_API int64_t sqk_tsv_heads(const char *text, const int64_t *line_begin, const int64_t *sig_begin, int64_t n_lines,
                               int n_cols, char *out, int64_t cap);
+/* The rows get_region_multi prints (MotifSeq.py:441-449) for a batch, floats written as Python's repr() writes them:
+ * heads = "fast5 <TAB> readID <NL>" per read (sqk_tsv_heads); names / consts = per model, NUL-separated (consts: the text of
+ * "mod_mean <TAB> mod_stdev"); hits [n_reads][n_models] sqk_hit; zs / ps / hps [n_reads][n_models] = Z-score, p-value,
+ * hit probability.  Reads whose hit is a status (start < 0) print nothing.  Returns the bytes written, or minus an upper
+ * bound of the bytes needed when cap is too small (out may be NULL to ask). */
+SQK_API int64_t sqk_tsv_format_rows(const char *heads, int64_t n_reads, const void *hits, int n_models, const char *names,
+                                    const char *consts, const double *zs, const double *ps, const double *hps, int n_threads,
+                                    char *out, int64_t cap);
 SQK_API int64_t sqk_tsv_format(const int16_t *samples, const int64_t *offsets, int64_t n_reads, const char *heads,
                                const int64_t *head_offsets, int n_threads, char *out, int64_t cap);
 

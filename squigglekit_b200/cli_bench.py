@@ -60,15 +60,19 @@ def generate(n_reads: int, n_samples: int, motif: np.ndarray, device=None, chunk
 
 
 def time_cli(script: str, argv, n_reads: int, timeout: float = 900.0):
-    """Run `python <script> argv...` with stdout to /dev/null -> dict(reads/s, seconds, rows)."""
+    """Run `python <script> argv...` with stdout captured -> dict(reads/s, seconds, rows).  With SQK_CLI_PROFILE set the
+    command line's own breakdown (its last stderr line) is returned as well."""
     t0 = time.perf_counter()
-    with open(os.devnull, "wb") as null:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, script), *argv], stdout=subprocess.PIPE, stderr=null, timeout=timeout)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, script), *argv], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
     dt = time.perf_counter() - t0
     if p.returncode != 0:
-        raise RuntimeError(f"{script} exited with {p.returncode}")
+        raise RuntimeError(f"{script} exited with {p.returncode}: {p.stderr[-300:]!r}")
     rows = p.stdout.count(b"\n")
-    return {"value": n_reads / dt, "unit": "reads/s", "seconds": dt, "rows_printed": rows}
+    out = {"value": n_reads / dt, "unit": "reads/s", "seconds": dt, "rows_printed": rows}
+    prof = [ln for ln in p.stderr.decode("utf-8", "replace").split("\n") if ln.startswith("sqk profile")]
+    if prof:
+        out["profile"] = prof[-1]
+    return out
 
 
 def cleanup(sig_path: str):

@@ -110,6 +110,25 @@ def format_rows(heads, names, hits, m, b, std, L):
     return rows, skipped
 
 
+def format_rows_bytes(heads_bytes, names, hits, m, b, std, L):
+    """format_rows for a batch whose head columns are still text (tsv.Batch.heads_bytes): the per-model constants and the
+    score arrays are computed here exactly as above, the text is written by libsqk.  -> (bytes, skipped [(read, code)])."""
+    from scipy.special import ndtr
+    from . import tsv
+    consts, zs, ps, hps = [], [], [], []
+    for c, name in enumerate(names):
+        mod_mean = (m * L[c]) + b
+        mod_stdev = mod_mean * std
+        dist = hits["dist"][:, c].astype(np.float64)
+        Z = (dist - mod_mean) / mod_stdev
+        p_value = ndtr(Z)
+        consts.append("{}\t{}".format(mod_mean, mod_stdev))
+        zs.append(Z); ps.append(p_value); hps.append((1 - p_value) * 100)
+    text = tsv.format_hit_rows(heads_bytes, hits, names, consts, np.stack(zs, axis=1), np.stack(ps, axis=1), np.stack(hps, axis=1))
+    bad = np.argwhere(hits["start"] < 0)
+    return text, [(int(r), int(hits["start"][r, c])) for r, c in bad]
+
+
 def _opener(path):
     return gzip.open if path.endswith('.gz') else open
 
@@ -231,18 +250,21 @@ def run_signal_file(ctx, args, model, m_order, L, out):
         for b in rd:
             t0 = time.perf_counter(); tm["parse"] += t0 - t_last
             if not b.status.any() and not args.sig_extract:
-                heads = [(h[0], h[1] if len(h) > 1 else "") for h in b.heads(2)]
+                heads = b.heads_bytes(2)
                 t1 = time.perf_counter(); tm["heads"] += t1 - t0
                 hits, _ = ctx.motifseq(b.signals[:int(b.offsets[b.n])], b.offsets, models, scale=args.scale,
                                        scale_low=args.scale_low, scale_hi=args.scale_hi, precision=args.precision, want_kept=False)
                 t2 = time.perf_counter(); tm["gpu"] += t2 - t1
-                rows, skipped = format_rows(heads, m_order, hits, args.slope, args.intercept, args.std_const, L)
+                text, skipped = format_rows_bytes(heads, m_order, hits, args.slope, args.intercept, args.std_const, L)
                 t3 = time.perf_counter(); tm["format"] += t3 - t2
-                for r, code in skipped:
-                    why = "no samples left after outlier removal" if code == -1 else "MAD is 0: med-MAD scaling undefined"
-                    sys.stderr.write("{} {}: {} - skipped\n".format(heads[r][0], heads[r][1], why))
-                if rows:
-                    out.write("\n".join(rows) + "\n")
+                if skipped:
+                    hl = heads.decode("utf-8", "replace").split("\n")
+                    for r, code in skipped:
+                        why = "no samples left after outlier removal" if code == -1 else "MAD is 0: med-MAD scaling undefined"
+                        sys.stderr.write("{}: {} - skipped\n".format(hl[r].replace("\t", " "), why))
+                if text:
+                    out.flush()
+                    (out.buffer if hasattr(out, "buffer") else out).write(text if hasattr(out, "buffer") else text.decode("utf-8", "replace"))
                 t_last = time.perf_counter(); tm["write"] += t_last - t3
                 continue
             batch = []

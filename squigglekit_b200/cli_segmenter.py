@@ -203,14 +203,22 @@ def emit(args, cfg, names, segs, nsegs, out):
 
 def run_signal_file(ctx, args, cfg, out):
     """-s input through the batched text reader (squigglekit_b200.tsv): batches of plain int16 lines go from the parsed
-    pinned buffer straight into one libsqk call; anything else in a batch takes the per-line path."""
+    pinned buffer straight into one libsqk call; anything else in a batch takes the per-line path.
+    SQK_CLI_PROFILE=1 prints where the wall-clock time went (stderr)."""
+    import time
     from . import tsv
+    tm = {"parse": 0.0, "heads": 0.0, "gpu": 0.0, "format": 0.0}
+    t_last = time.perf_counter()
     with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
         for b in rd:
+            t0 = time.perf_counter(); tm["parse"] += t0 - t_last
             if not b.status.any():
                 names = [h[0] for h in b.heads(1)]
+                t1 = time.perf_counter(); tm["heads"] += t1 - t0
                 segs, nsegs = segment_batch(ctx, b.signals[:int(b.offsets[b.n])], b.offsets, cfg)
+                t2 = time.perf_counter(); tm["gpu"] += t2 - t1
                 emit(args, cfg, names, segs, nsegs, out)
+                t_last = time.perf_counter(); tm["format"] += t_last - t2
                 continue
             batch = []
             for i in range(b.n):
@@ -235,6 +243,9 @@ def run_signal_file(ctx, args, cfg, out):
                 else:
                     batch.append((fast5, sig.astype(np.float64), 0.0, 1.0))
             flush(ctx, args, cfg, batch, out)
+            t_last = time.perf_counter()
+    if os.environ.get("SQK_CLI_PROFILE"):
+        sys.stderr.write("\nsqk profile (s): " + ", ".join("{} {:.3f}".format(k, v) for k, v in tm.items()) + "\n")
 
 
 def main(argv=None):

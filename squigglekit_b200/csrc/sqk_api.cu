@@ -103,6 +103,7 @@ struct Slot {                 // everything one in-flight chunk needs
     DevBuf signals, offsets, stats, hits, nkept, segs, nsegs, counter, gstage, pa_off, pa_scale, ynorm, codes;
     DevBuf jobs, fbjobs, lbreads, jobres;   // two-pass DTW plan (sqk_dtw_plan.cuh)
     DevBuf redo, mask, rm_p, rm_masks, bnd_a, bnd_b, jobs2, rtjobs, pending;        // sqk_stats2_kernel: redo list ([0] = length, entries from [4]); segmenter bit masks
+    HostBuf hin;              // a PAGEABLE caller buffer is brought here (pinned) by all host threads before its H2D copy
     HostBuf hout[2];          // results land here (pinned) so the D2H copy never blocks the host ...
     Pending pend[2];          // ... and move to the caller's (possibly pageable) arrays when the slot is recycled
     int n_pend = 0;
@@ -113,6 +114,25 @@ static bool is_pinned(const void *p)
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" void sqk_parallel_memcpy(void *dst, const void *src, size_t bytes, int n_threads);   // sqk_tsv.cpp (OpenMP)
+
+// caller's host samples -> device.  A pinned source goes out as one asynchronous copy.  A pageable one would be staged by
+// the driver through its own pinned buffer on ONE thread (~10 GB/s: the call is then 4-5x slower than the PCIe bound); it
+// is copied into the slot's pinned staging buffer by all host threads instead (the slot's previous chunk is done: recycle),
+// and that copy overlaps the other slot's transfers and kernels.
+static int signals_to_device(Slot &s, cudaStream_t st, void *dst, const void *src, size_t bytes, bool src_pinned)
+{
+    if (bytes == 0) return SQK_OK;
+    if (src_pinned) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return SQK_OK;
+    }
+    TRY(ensure_host(s.hin, bytes));
+    sqk_parallel_memcpy(s.hin.p, src, bytes, 0);
+    CU(cudaMemcpyAsync(dst, s.hin.p, bytes, cudaMemcpyHostToDevice, st));
+    return SQK_OK;
 }
 
 // device -> caller's host array, without stalling the pipeline when that array is pageable
@@ -1218,6 +1238,7 @@ int sqk_ctx_destroy(sqk_ctx *c)
         Slot &s = c->slot[i];
         release(s.signals); release(s.offsets); release(s.stats); release(s.hits); release(s.nkept);
         release(s.segs); release(s.nsegs); release(s.counter); release(s.gstage); release(s.pa_off); release(s.pa_scale); release(s.ynorm); release(s.codes); release(s.rm_p); release(s.rm_masks); release(s.bnd_a); release(s.bnd_b); release(s.jobs2); release(s.rtjobs); release(s.pending);
+        if (s.hin.p) { cudaFreeHost(s.hin.p); s.hin.p = nullptr; s.hin.cap = 0; }
         release(s.jobs); release(s.fbjobs); release(s.lbreads); release(s.jobres); release(s.redo); release(s.mask);
         for (int k = 0; k < 2; k++) if (s.hout[k].p) cudaFreeHost(s.hout[k].p);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -1518,7 +1539,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
     TRY(upload_models(c, models, model_points, c->slot[0].stream));
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
-    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept), sig_pinned = signals && is_pinned(signals);
     PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
@@ -1530,7 +1551,7 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
         TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
         TRY(ensure(s.hits, (size_t)nr * n_models * sizeof(sqk_hit)));
         TRY(ensure(s.nkept, (size_t)nr * sizeof(int32_t)));
-        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        TRY(signals_to_device(s, st, s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), sig_pinned));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         View v{(const int16_t *)s.signals.p - s0, s0, s1, (const int64_t *)s.offsets.p - r0, r0, nr, maxlen};
         TRY(enqueue_motifseq(c, s, st, v, (const double *)c->model.p, models, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
@@ -1587,7 +1608,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
     if (maxlen > 0x7fffffffLL) return fail(SQK_ERR_UNSUPPORTED, "a read has more than 2^31-1 samples");
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, c->chunk_samples > 0 ? c->chunk_samples : chunk_samples(), cuts);
-    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs), sig_pinned = signals && is_pinned(signals);
     TRY(host_begin(c));
     PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
@@ -1600,7 +1621,7 @@ static int segmenter_impl(sqk_ctx *c, const int16_t *signals, const int64_t *off
         TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
         TRY(ensure(s.segs, (size_t)nr * seg_row));
         TRY(ensure(s.nsegs, (size_t)nr * sizeof(int32_t)));
-        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        TRY(signals_to_device(s, st, s.signals.p, signals + s0, (size_t)ns * sizeof(int16_t), sig_pinned));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(s.segs.p, 0, (size_t)nr * seg_row, st));
         const double *d_po = nullptr, *d_ps = nullptr;
@@ -1661,7 +1682,7 @@ int sqk_motifseq_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, 
     TRY(upload_models(c, models, model_points, c->slot[0].stream));
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
-    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept);
+    const bool hits_pinned = is_pinned(hits), nkept_pinned = n_kept && is_pinned(n_kept), sig_pinned = signals && is_pinned(signals);
     PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         Slot &s = c->slot[ci & 1];
@@ -1673,7 +1694,7 @@ int sqk_motifseq_f64(sqk_ctx *c, const double *signals, const int64_t *offsets, 
         TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
         TRY(ensure(s.hits, (size_t)nr * n_models * sizeof(sqk_hit)));
         TRY(ensure(s.nkept, (size_t)nr * sizeof(int32_t)));
-        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, st));
+        TRY(signals_to_device(s, st, s.signals.p, signals + s0, (size_t)ns * sizeof(double), sig_pinned));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         View64 v{(const double *)s.signals.p - s0, (const int64_t *)s.offsets.p - r0, r0, nr, s0, ns};
         TRY(enqueue_motifseq_f64(c, s, st, v, (const double *)c->model.p, model_offsets, n_models, p, (sqk_hit *)s.hits.p,
@@ -1715,7 +1736,7 @@ int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets,
         if (offsets[r + 1] < offsets[r]) return fail(SQK_ERR_ARG, "offsets are not non-decreasing at read %lld", (long long)r);
     std::vector<int64_t> cuts;
     plan_chunks(offsets, n_reads, std::max<int64_t>((c->chunk_samples > 0 ? c->chunk_samples : chunk_samples()) / 4, 1), cuts);
-    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs);
+    const bool segs_pinned = is_pinned(segs), nsegs_pinned = is_pinned(n_segs), sig_pinned = signals && is_pinned(signals);
     TRY(host_begin(c));
     PipeGuard pg(c);
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
@@ -1728,7 +1749,7 @@ int sqk_segmenter_f64(sqk_ctx *c, const double *signals, const int64_t *offsets,
         TRY(ensure(s.offsets, (size_t)(nr + 1) * sizeof(int64_t)));
         TRY(ensure(s.segs, (size_t)nr * seg_row));
         TRY(ensure(s.nsegs, (size_t)nr * sizeof(int32_t)));
-        if (ns > 0) CU(cudaMemcpyAsync(s.signals.p, signals + s0, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, st));
+        TRY(signals_to_device(s, st, s.signals.p, signals + s0, (size_t)ns * sizeof(double), sig_pinned));
         CU(cudaMemcpyAsync(s.offsets.p, offsets + r0, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(s.segs.p, 0, (size_t)nr * seg_row, st));
         View64 v{(const double *)s.signals.p - s0, (const int64_t *)s.offsets.p - r0, r0, nr, s0, ns};

@@ -8,7 +8,10 @@
 // both in parallel over the lines (OpenMP) -- straight into the int16 batch the GPU path consumes.  Lines that are not
 // plain int16 integers (pA output, exponents, empty fields) are flagged, not guessed at: the caller sends them through the
 // float path.  No GPU work in this file; it is part of libsqk.so so that one ctypes handle serves the whole drop-in.
+#include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -17,8 +20,37 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <sched.h>
 
 #include "../../include/sqk.h"
+
+// host threads this process may run on (NOT OMP_NUM_THREADS: launchers such as torch.distributed.run set that to 1)
+static int host_threads(int asked)
+{
+    if (asked > 0) return asked;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n < 1) n = 1;
+    return n > 64 ? 64 : n;
+}
+
+// memcpy on all host threads (1 MiB pieces): what sqk_api.cu uses to bring a PAGEABLE caller buffer into its pinned
+// staging buffer -- the driver's own staging of pageable memory runs on one thread
+extern "C" void sqk_parallel_memcpy(void *dst, const void *src, size_t bytes, int n_threads)
+{
+    const size_t piece = (size_t)1 << 20;
+    const int64_t n = (int64_t)((bytes + piece - 1) / piece);
+    int nt = host_threads(n_threads);
+    if (nt > 16) nt = 16;                                       // memory bandwidth, not cores, limits this
+    if (n <= 1 || nt <= 1) { memcpy(dst, src, bytes); return; }
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t i = 0; i < n; i++) {
+        const size_t at = (size_t)i * piece;
+        memcpy((char *)dst + at, (const char *)src + at, bytes - at < piece ? bytes - at : piece);
+    }
+}
 
 // parse one line's signal part [p, e) into out[0..n_fields); returns the status bits
 static int parse_fields_i16(const char *p, const char *e, int16_t *out, int64_t n_fields)
@@ -79,7 +111,7 @@ int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int start_col
         n++;
     }
 #ifdef _OPENMP
-    const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+    const int nt = host_threads(n_threads);
 #else
     const int nt = 1; (void)n_threads;
 #endif
@@ -156,6 +188,133 @@ int64_t sqk_tsv_heads(const char *text, const int64_t *line_begin, const int64_t
     return need;
 }
 
+// Python's repr() of a float (= str() of a numpy float64): the shortest digit string that reads back as the same double,
+// fixed notation with at least ".0" when 1e-4 <= |x| < 1e16, otherwise d.ddde+XX with at least two exponent digits
+// (CPython: PyOS_double_to_string(x, 'r', 0, Py_DTSF_ADD_DOT_0), float_repr_style "short").  The shortest string has at
+// most 17 significant digits.  If it has <= 15, the correctly rounded 15-digit decimal IS that string padded with zeros
+// (a normal double lies within 1.2e-16 relative of it, less than half a unit of the 15th digit), so: print 15 digits, read
+// back, strip zeros; else the correctly rounded 16-digit decimal if it reads back (the closest of the 16-digit candidates,
+// which is the one repr picks), else the correctly rounded 17-digit one.  Returns the length written; buf needs 32 bytes.
+static int fmt_repr(double x, char *buf)
+{
+    if (x != x) { memcpy(buf, "nan", 3); return 3; }
+    if (isinf(x)) { if (x > 0) { memcpy(buf, "inf", 3); return 3; } memcpy(buf, "-inf", 4); return 4; }
+    char *w = buf;
+    if (signbit(x)) { *w++ = '-'; x = -x; }
+    if (x == 0.0) { memcpy(w, "0.0", 3); return (int)(w - buf) + 3; }
+    char e[40];
+    if (x < 2.3e-308) {                                       // subnormal: few significant bits, try every length
+        for (int p = 0; p <= 16; p++) { snprintf(e, sizeof(e), "%.*e", p, x); if (strtod(e, nullptr) == x) break; }
+    } else {
+        snprintf(e, sizeof(e), "%.14e", x);                   // d.dddddddddddddde+XX
+        if (strtod(e, nullptr) != x) {
+            snprintf(e, sizeof(e), "%.15e", x);
+            if (strtod(e, nullptr) != x) snprintf(e, sizeof(e), "%.16e", x);
+        }
+    }
+    char *ep = strchr(e, 'e');
+    const int exp10 = atoi(ep + 1);
+    char dig[20];
+    int nd = 0;
+    for (const char *q = e; q < ep; q++) if (*q != '.') dig[nd++] = *q;
+    while (nd > 1 && dig[nd - 1] == '0') nd--;
+    if (exp10 >= -4 && exp10 < 16) {
+        if (exp10 < 0) {                                      // 0.000ddd
+            *w++ = '0'; *w++ = '.';
+            for (int i = 0; i < -exp10 - 1; i++) *w++ = '0';
+            memcpy(w, dig, (size_t)nd); w += nd;
+        } else {
+            for (int i = 0; i <= exp10; i++) *w++ = i < nd ? dig[i] : '0';
+            *w++ = '.';
+            if (nd > exp10 + 1) { memcpy(w, dig + exp10 + 1, (size_t)(nd - exp10 - 1)); w += nd - exp10 - 1; }
+            else *w++ = '0';
+        }
+    } else {
+        *w++ = dig[0];
+        if (nd > 1) { *w++ = '.'; memcpy(w, dig + 1, (size_t)(nd - 1)); w += nd - 1; }
+        *w++ = 'e';
+        *w++ = exp10 < 0 ? '-' : '+';
+        const int ae = exp10 < 0 ? -exp10 : exp10;
+        if (ae >= 100) *w++ = (char)('0' + ae / 100);
+        *w++ = (char)('0' + (ae / 10) % 10);
+        *w++ = (char)('0' + ae % 10);
+    }
+    return (int)(w - buf);
+}
+
+static int fmt_int(int v, char *buf)
+{
+    char tmp[12];
+    int nd = 0, n = 0;
+    unsigned u = v < 0 ? (unsigned)(-(int64_t)v) : (unsigned)v;
+    if (v < 0) buf[n++] = '-';
+    do { tmp[nd++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (nd) buf[n++] = tmp[--nd];
+    return n;
+}
+
+// The rows get_region_multi prints (MotifSeq.py:441-449) for a batch, as text:
+//   head <TAB> name <TAB> start <TAB> end <TAB> end-start <TAB> dist <TAB> consts <TAB> Z <TAB> p <TAB> hit_P <NL>
+// heads: "fast5 <TAB> readID <NL>" per read (sqk_tsv_heads); names / consts ("mod_mean <TAB> mod_stdev" already as text):
+// per model, NUL-separated; hits [n_reads][n_models] (start, end, dist); zs / ps / hps [n_reads][n_models].  Reads whose
+// hit is a status (start < 0) print nothing.  Floats are written as Python's repr() writes them.  Returns the bytes
+// written, or minus an upper bound of the bytes needed when cap is too small.
+int64_t sqk_tsv_format_rows(const char *heads, int64_t n_reads, const void *hits_v, int n_models, const char *names,
+                            const char *consts, const double *zs, const double *ps, const double *hps, int n_threads,
+                            char *out, int64_t cap)
+{
+    struct Hit { int32_t start, end; double dist; };
+    const Hit *hits = (const Hit *)hits_v;
+    if (!heads || !hits || !names || !consts || !zs || !ps || !hps || n_reads < 0 || n_models < 1) return 0;
+    std::vector<const char *> nm((size_t)n_models), cs((size_t)n_models);
+    std::vector<size_t> nml((size_t)n_models), csl((size_t)n_models);
+    { const char *p = names, *q = consts;
+      for (int m = 0; m < n_models; m++) { nm[(size_t)m] = p; nml[(size_t)m] = strlen(p); p += nml[(size_t)m] + 1;
+                                           cs[(size_t)m] = q; csl[(size_t)m] = strlen(q); q += csl[(size_t)m] + 1; } }
+    // where each read's head starts, and an upper bound of each read's text
+    std::vector<int64_t> hb((size_t)n_reads + 1), at((size_t)n_reads + 1);
+    { const char *p = heads;
+      for (int64_t r = 0; r < n_reads; r++) { hb[(size_t)r] = p - heads; const char *nl = strchr(p, '\n'); p = nl ? nl + 1 : p + strlen(p); }
+      hb[(size_t)n_reads] = p - heads; }
+    at[0] = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        int64_t need = 0;
+        for (int m = 0; m < n_models; m++) need += (hb[(size_t)r + 1] - hb[(size_t)r]) + (int64_t)nml[(size_t)m] + (int64_t)csl[(size_t)m] + 3 * 12 + 4 * 26 + 12;
+        at[(size_t)r + 1] = at[(size_t)r] + need;
+    }
+    if (!out || at[(size_t)n_reads] > cap) return -at[(size_t)n_reads];
+    std::vector<int64_t> len((size_t)n_reads);
+    const int nt = host_threads(n_threads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t r = 0; r < n_reads; r++) {
+        char *w = out + at[(size_t)r];
+        const int64_t hl = hb[(size_t)r + 1] - hb[(size_t)r] - 1;        // without the newline
+        for (int m = 0; m < n_models; m++) {
+            const Hit &h = hits[r * n_models + m];
+            if (h.start < 0) continue;
+            memcpy(w, heads + hb[(size_t)r], (size_t)(hl > 0 ? hl : 0)); w += hl > 0 ? hl : 0;
+            *w++ = '\t'; memcpy(w, nm[(size_t)m], nml[(size_t)m]); w += nml[(size_t)m];
+            *w++ = '\t'; w += fmt_int(h.start, w);
+            *w++ = '\t'; w += fmt_int(h.end, w);
+            *w++ = '\t'; w += fmt_int(h.end - h.start, w);
+            *w++ = '\t'; w += fmt_repr(h.dist, w);
+            *w++ = '\t'; memcpy(w, cs[(size_t)m], csl[(size_t)m]); w += csl[(size_t)m];
+            *w++ = '\t'; w += fmt_repr(zs[r * n_models + m], w);
+            *w++ = '\t'; w += fmt_repr(ps[r * n_models + m], w);
+            *w++ = '\t'; w += fmt_repr(hps[r * n_models + m], w);
+            *w++ = '\n';
+        }
+        len[(size_t)r] = w - (out + at[(size_t)r]);
+    }
+    // close the gaps (each read was given an upper bound of room)
+    int64_t total = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        if (at[(size_t)r] != total) memmove(out + total, out + at[(size_t)r], (size_t)len[(size_t)r]);
+        total += len[(size_t)r];
+    }
+    return total;
+}
+
 // "fast5 \t readID \t s0 \t s1 ...\n" per read (SquigglePull.py:251-253).  heads: the text in front of the signal columns of
 // each read ("fast5\treadID" or with the four extra_info columns), concatenated, head_offsets[n_reads + 1].  Returns the
 // bytes written, or the (negative) bytes needed when `cap` is too small.
@@ -166,7 +325,7 @@ int64_t sqk_tsv_format(const int16_t *samples, const int64_t *offsets, int64_t n
     std::vector<int64_t> at((size_t)n_reads + 1);
     at[0] = 0;
 #ifdef _OPENMP
-    const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+    const int nt = host_threads(n_threads);
 #else
     const int nt = 1; (void)n_threads;
 #endif

@@ -43,17 +43,21 @@ class Batch:
             b = bytes(self.text[int(self.line_begin[i]):int(self.line_begin[i + 1])]).rstrip(b"\r\n")
         return b.decode("utf-8", "replace").split("\t")
 
-    def heads(self, n_cols: int = 2):
-        """-> list of lists: the first ``n_cols`` columns of every line."""
+    def heads_bytes(self, n_cols: int = 2) -> bytes:
+        """The first ``n_cols`` columns of every line, ``c0 <TAB> c1 <NL>`` each (one C call for the batch)."""
         lib = _cabi.lib()
         need = -int(lib.sqk_tsv_heads(self.base, self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.n, n_cols, None, 0))
         if need <= 0:
-            return []
+            return b""
         out = bytearray(need)
         view = (C.c_char * need).from_buffer(out)
         lib.sqk_tsv_heads(self.base, self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.n, n_cols, C.addressof(view), need)
         del view
-        return [ln.split("\t") for ln in out.decode("utf-8", "replace").split("\n")[:self.n]]
+        return bytes(out)
+
+    def heads(self, n_cols: int = 2):
+        """-> list of lists: the first ``n_cols`` columns of every line."""
+        return [ln.split("\t") for ln in self.heads_bytes(n_cols).decode("utf-8", "replace").split("\n")[:self.n]]
 
     def tail_text(self, i: int) -> str:
         return bytes(self.text[int(self.sig_begin[i]):int(self.line_begin[i + 1])]).rstrip(b"\r\n").decode("utf-8", "replace")
@@ -219,3 +223,27 @@ def format_reads(heads, signals: np.ndarray, offsets: np.ndarray, n_threads: int
 
 def write_reads(fh, heads, signals, offsets, n_threads: int = 0):
     fh.write(format_reads(heads, signals, offsets, n_threads))
+
+
+def format_hit_rows(heads: bytes, hits: np.ndarray, names, consts, zs: np.ndarray, ps: np.ndarray, hps: np.ndarray,
+                    n_threads: int = 0) -> bytes:
+    """The rows get_region_multi prints (MotifSeq.py:441-449) for a batch, formatted by libsqk (``sqk_tsv_format_rows``):
+    heads = ``Batch.heads_bytes(2)``; hits structured [n_reads, n_models]; names / consts: per model, the motif name and the
+    text of ``mod_mean <TAB> mod_stdev``; zs / ps / hps float64 [n_reads, n_models].  Floats come out as Python's repr()."""
+    lib = _cabi.lib()
+    n, m = hits.shape
+    hits = np.ascontiguousarray(hits)
+    zs, ps, hps = (np.ascontiguousarray(a, dtype=np.float64) for a in (zs, ps, hps))
+    nb = b"".join(x.encode() + b"\0" for x in names)
+    cb = b"".join(x.encode() + b"\0" for x in consts)
+    heads = heads + b"\0"
+    need = -int(lib.sqk_tsv_format_rows(heads, n, hits.ctypes.data, m, nb, cb, zs.ctypes.data, ps.ctypes.data, hps.ctypes.data,
+                                        n_threads, None, 0))
+    if need <= 0:
+        return b""
+    out = bytearray(need)
+    view = (C.c_char * need).from_buffer(out)
+    got = int(lib.sqk_tsv_format_rows(heads, n, hits.ctypes.data, m, nb, cb, zs.ctypes.data, ps.ctypes.data, hps.ctypes.data,
+                                      n_threads, C.addressof(view), need))
+    del view
+    return bytes(out[:got])

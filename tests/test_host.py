@@ -126,3 +126,27 @@ def test_vectorised_rows_equal_the_per_read_rows():
                                                 0.08468, L[c]))
     assert rows == want
     assert sorted(skipped) == [(7, -1), (9, -2)]
+    # ... and so does the formatter in libsqk (floats as Python's repr writes them)
+    hb = ("\n".join(f"{a}\t{b}" for a, b in heads) + "\n").encode()
+    text, skipped_c = cli_motifseq.format_rows_bytes(hb, names, hits, 2.90, -9.6, 0.08468, L)
+    assert text == ("\n".join(want) + "\n").encode()
+    assert sorted(skipped_c) == [(7, -1), (9, -2)]
+
+
+def test_repr_of_floats_in_libsqk():
+    """sqk_tsv_format_rows writes a double exactly as Python's repr() does: shortest round-trip digits, fixed notation
+    in [1e-4, 1e16), exponents with at least two digits, subnormals, infinities."""
+    import squigglekit_b200 as sqk
+    from squigglekit_b200 import tsv
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.normal(0, 1, 60000) * 10.0 ** rng.integers(-30, 30, 60000), rng.integers(-10**6, 10**6, 5000).astype(float),
+                         rng.integers(-10**6, 10**6, 5000) / 1000.0, rng.random(20000), np.ldexp(rng.random(3000), rng.integers(-1074, -1000, 3000)),
+                         np.array([0.0, -0.0, 0.1, 0.2, 0.3, 1 / 3, 1e15, 1e16, 1e17, 123456.789, 5e-5, 1e-5, 0.0001, 0.001, 5e-324, 1.7976931348623157e308,
+                                   2.2250738585072014e-308, 9007199254740993.0, 0.30000000000000004, np.inf, -np.inf, 1e22, 1e23, 1e100, 1e-100])])
+    hits = np.zeros((xs.size, 1), dtype=sqk.HIT_DTYPE)
+    hits["dist"][:, 0] = xs; hits["end"] = 1
+    out = tsv.format_hit_rows(b"h\n" * xs.size, hits, ["n"], ["c"], xs[:, None], xs[:, None], xs[:, None]).split(b"\n")[:-1]
+    assert len(out) == xs.size
+    for x, line in zip(xs.tolist(), out):
+        f = line.decode().split("\t")
+        assert f[5] == repr(x) and f[7] == repr(x) and f[9] == repr(x), (x, f)

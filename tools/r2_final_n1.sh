@@ -5,7 +5,7 @@ set -u
 O=gpurun_out/r2final; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $O/smi.txt
 timeout 1800 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu.log
-timeout 900 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -2 $O/bench_n1.err
+SQK_CLI_PROFILE=1 timeout 900 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -2 $O/bench_n1.err
 timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; echo "ref rc=$?"
 timeout 300 python bench.py --plan single_pass --no-cpu-baseline --no-extras > $O/bench_single_pass.json 2> /dev/null; echo "single-pass rc=$?"
 timeout 300 python bench.py --scale medmad --no-cpu-baseline --no-extras --no-e2e > $O/bench_medmad.json 2> /dev/null; echo "medmad rc=$?"
@@ -18,9 +18,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:s
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $O/under_ncu.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sqk_ -c 40 --csv --log-file $O/launches_segmenter.csv \
     python tools/bench_segmenter.py --reads 1000000 --steps 1 --no-e2e > /dev/null 2>&1; echo "seg launch list rc=$?"
-cap() { # name regex skip cmd...
+cap() { # name regex skip cmd...   (the .ncu-rep is summarised on the box and removed: gpurun brings back <= 64 MiB)
   local name=$1 rx=$2 skip=$3; shift 3
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o $O/$name "$@" > /dev/null 2>&1; echo "ncu $name rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o /tmp/$name "$@" > /dev/null 2>&1; echo "ncu $name rc=$?"
+  python tools/ncu_summary.py /tmp/$name.ncu-rep > $O/${name}_ncu_full.txt 2>&1
+  python tools/ncu_lines.py /tmp/$name.ncu-rep > $O/${name}_ncu_lines.txt 2>&1
 }
 cap lb sqk_dtw_lb_kernel 3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras
 cap win sqk_dtw_kernel 6 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras
