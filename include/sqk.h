@@ -262,6 +262,11 @@ SQK_API int64_t sqk_tsv_heads(const char *text, const int64_t *line_begin, const
 SQK_API int64_t sqk_tsv_format_rows(const char *heads, int64_t n_reads, const void *hits, int n_models, const char *names,
                                     const char *consts, const double *zs, const double *ps, const double *hps, int n_threads,
                                     char *out, int64_t cap);
+/* The rows segmenter.py prints (segmenter.py:130-146: name <TAB> s0,e0,s1,e1,...) for the reads with keep[r] != 0; heads =
+ * "name <NL>" per read (sqk_tsv_heads, one column); segs [n_reads][max_segs][2], n_segs [n_reads] as sqk_segmenter returns
+ * them.  Returns the bytes written, or minus an upper bound of the bytes needed when cap is too small / out is NULL. */
+SQK_API int64_t sqk_tsv_format_segs(const char *heads, int64_t n_reads, const int32_t *segs, const int32_t *n_segs, int max_segs,
+                                    const unsigned char *keep, int n_threads, char *out, int64_t cap);
 SQK_API int64_t sqk_tsv_format(const int16_t *samples, const int64_t *offsets, int64_t n_reads, const char *heads,
                                const int64_t *head_offsets, int n_threads, char *out, int64_t cap);
 

@@ -201,6 +201,36 @@ def emit(args, cfg, names, segs, nsegs, out):
         out.write("\n".join(lines) + "\n")
 
 
+def emit_batch(args, cfg, heads_bytes, segs, nsegs, out):
+    """emit() for a batch whose names are still text (tsv.Batch.heads_bytes(1)): the -k / -g tests of test_segs
+    (segmenter.py:473-494) on arrays, the rows written by libsqk; the reference's stderr notes for the reads it drops."""
+    from . import tsv
+    n = nsegs.shape[0]
+    has = nsegs > 0
+    first_start = segs[:, 0, 0]
+    late = has & (first_start > args.stall_start) if cfg.stall else np.zeros(n, dtype=bool)
+    far = np.zeros(n, dtype=bool)
+    if cfg.gap and segs.shape[1] > 1:
+        far = (nsegs > 1) & (segs[:, 1, 0] > segs[:, 0, 1] + args.gap_dist)
+    keep = has.copy()
+    if args.test:
+        keep &= ~late & ~far
+    if not has.all() or (args.test and (late.any() or far.any())):
+        names = heads_bytes.decode("utf-8", "replace").split("\n")
+        for r in np.flatnonzero(~has):
+            sys.stderr.write("no segments found: {}".format(names[r]))
+        if args.test:
+            for r in np.flatnonzero(has & (late | far)):
+                sys.stderr.write("start seg too late!" if (cfg.stall and late[r]) else "second seg too far!")
+    text = tsv.format_seg_rows(heads_bytes, segs, nsegs, keep)
+    if text:
+        out.flush()
+        if hasattr(out, "buffer"):
+            out.buffer.write(text)
+        else:
+            out.write(text.decode("utf-8", "replace"))
+
+
 def run_signal_file(ctx, args, cfg, out):
     """-s input through the batched text reader (squigglekit_b200.tsv): batches of plain int16 lines go from the parsed
     pinned buffer straight into one libsqk call; anything else in a batch takes the per-line path.
@@ -213,11 +243,11 @@ def run_signal_file(ctx, args, cfg, out):
         for b in rd:
             t0 = time.perf_counter(); tm["parse"] += t0 - t_last
             if not b.status.any():
-                names = [h[0] for h in b.heads(1)]
+                heads = b.heads_bytes(1)
                 t1 = time.perf_counter(); tm["heads"] += t1 - t0
                 segs, nsegs = segment_batch(ctx, b.signals[:int(b.offsets[b.n])], b.offsets, cfg)
                 t2 = time.perf_counter(); tm["gpu"] += t2 - t1
-                emit(args, cfg, names, segs, nsegs, out)
+                emit_batch(args, cfg, heads, segs, nsegs, out)
                 t_last = time.perf_counter(); tm["format"] += t_last - t2
                 continue
             batch = []

@@ -315,6 +315,50 @@ int64_t sqk_tsv_format_rows(const char *heads, int64_t n_reads, const void *hits
     return total;
 }
 
+// The rows segmenter.py prints (segmenter.py:130-146: name <TAB> s0,e0,s1,e1,...) for the reads with keep[r] != 0.
+// heads: "name <NL>" per read (sqk_tsv_heads with one column); segs [n_reads][max_segs][2], n_segs [n_reads].  Returns the
+// bytes written, or minus an upper bound of the bytes needed when cap is too small (out may be NULL to ask).
+int64_t sqk_tsv_format_segs(const char *heads, int64_t n_reads, const int32_t *segs, const int32_t *n_segs, int max_segs,
+                            const unsigned char *keep, int n_threads, char *out, int64_t cap)
+{
+    if (!heads || !segs || !n_segs || !keep || n_reads < 0 || max_segs < 1) return 0;
+    std::vector<int64_t> hb((size_t)n_reads + 1), at((size_t)n_reads + 1), len((size_t)n_reads);
+    { const char *p = heads;
+      for (int64_t r = 0; r < n_reads; r++) { hb[(size_t)r] = p - heads; const char *nl = strchr(p, '\n'); p = nl ? nl + 1 : p + strlen(p); }
+      hb[(size_t)n_reads] = p - heads; }
+    at[0] = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int n = n_segs[r] < max_segs ? n_segs[r] : max_segs;
+        at[(size_t)r + 1] = at[(size_t)r] + (keep[r] ? (hb[(size_t)r + 1] - hb[(size_t)r]) + 2 + 24ll * (n > 0 ? n : 0) : 0);
+    }
+    if (!out || at[(size_t)n_reads] > cap) return -at[(size_t)n_reads];
+    const int nt = host_threads(n_threads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t r = 0; r < n_reads; r++) {
+        char *w = out + at[(size_t)r];
+        if (keep[r]) {
+            const int64_t hl = hb[(size_t)r + 1] - hb[(size_t)r] - 1;
+            memcpy(w, heads + hb[(size_t)r], (size_t)(hl > 0 ? hl : 0)); w += hl > 0 ? hl : 0;
+            *w++ = '\t';
+            const int n = n_segs[r] < max_segs ? n_segs[r] : max_segs;
+            for (int i = 0; i < n; i++) {
+                if (i) *w++ = ',';
+                w += fmt_int(segs[(r * max_segs + i) * 2], w);
+                *w++ = ',';
+                w += fmt_int(segs[(r * max_segs + i) * 2 + 1], w);
+            }
+            *w++ = '\n';
+        }
+        len[(size_t)r] = w - (out + at[(size_t)r]);
+    }
+    int64_t total = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        if (len[(size_t)r] && at[(size_t)r] != total) memmove(out + total, out + at[(size_t)r], (size_t)len[(size_t)r]);
+        total += len[(size_t)r];
+    }
+    return total;
+}
+
 // "fast5 \t readID \t s0 \t s1 ...\n" per read (SquigglePull.py:251-253).  heads: the text in front of the signal columns of
 // each read ("fast5\treadID" or with the four extra_info columns), concatenated, head_offsets[n_reads + 1].  Returns the
 // bytes written, or the (negative) bytes needed when `cap` is too small.

@@ -247,3 +247,23 @@ def format_hit_rows(heads: bytes, hits: np.ndarray, names, consts, zs: np.ndarra
                                       n_threads, C.addressof(view), need))
     del view
     return bytes(out[:got])
+
+
+def format_seg_rows(heads: bytes, segs: np.ndarray, n_segs: np.ndarray, keep: np.ndarray, n_threads: int = 0) -> bytes:
+    """The rows segmenter.py prints (``name <TAB> s0,e0,s1,e1,...``, segmenter.py:130-146) for the reads with ``keep``;
+    heads = ``Batch.heads_bytes(1)``; segs [n_reads, max_segs, 2] / n_segs [n_reads] as ``Context.segmenter`` returns them."""
+    lib = _cabi.lib()
+    segs = np.ascontiguousarray(segs, dtype=np.int32)
+    n_segs = np.ascontiguousarray(n_segs, dtype=np.int32)
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    n, cap_segs = segs.shape[0], segs.shape[1]
+    heads = heads + b"\0"
+    need = -int(lib.sqk_tsv_format_segs(heads, n, segs.ctypes.data, n_segs.ctypes.data, cap_segs, keep.ctypes.data, n_threads, None, 0))
+    if need <= 0:
+        return b""
+    out = bytearray(need)
+    view = (C.c_char * need).from_buffer(out)
+    got = int(lib.sqk_tsv_format_segs(heads, n, segs.ctypes.data, n_segs.ctypes.data, cap_segs, keep.ctypes.data, n_threads,
+                                      C.addressof(view), need))
+    del view
+    return bytes(out[:got])

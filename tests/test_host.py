@@ -150,3 +150,32 @@ def test_repr_of_floats_in_libsqk():
     for x, line in zip(xs.tolist(), out):
         f = line.decode().split("\t")
         assert f[5] == repr(x) and f[7] == repr(x) and f[9] == repr(x), (x, f)
+
+
+def test_segmenter_rows_batched_equal_per_read(capsys):
+    """cli_segmenter.emit_batch (arrays + libsqk's row writer) prints what emit prints read by read, for every combination of
+    the -u / -k / -g switches."""
+    import io
+    import types
+    import squigglekit_b200 as sqk
+    from squigglekit_b200 import cli_segmenter
+    rng = np.random.default_rng(21)
+    n, cap = 400, 6
+    nsegs = rng.integers(0, cap + 1, n).astype(np.int32)
+    segs = np.zeros((n, cap, 2), np.int32)
+    for r in range(n):
+        pos = np.sort(rng.integers(0, 9000, 2 * cap))
+        segs[r] = pos.reshape(cap, 2)
+        segs[r, nsegs[r]:] = 0
+    names = [f"read_{i}.fast5" for i in range(n)]
+    hb = ("\n".join(names) + "\n").encode()
+    for test in (False, True):
+        for stall in (False, True):
+            for gap in (False, True):
+                args = types.SimpleNamespace(test=test, stall=stall, gap=gap, stall_start=300, gap_dist=3000)
+                cfg = sqk.SegConfig(stall=stall, gap=gap, stall_start=300, gap_dist=3000, max_segs=cap)
+                a, b = io.StringIO(), io.StringIO()
+                cli_segmenter.emit(args, cfg, names, segs, nsegs, a)
+                cli_segmenter.emit_batch(args, cfg, hb, segs, nsegs, b)
+                assert a.getvalue() == b.getvalue() and a.getvalue().count("\n") > 50
+    capsys.readouterr()
