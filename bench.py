@@ -90,6 +90,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    def wait_first(self, timeout: float = 15.0):
+        """Block until the first sample has arrived (nvidia-smi takes seconds to start on an 8-GPU box; a timed region
+        of a few steps would otherwise be over before the sampler has said anything).  Called outside the timed region."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def mark(self):
         self.t0, self.t1 = time.perf_counter(), None
 
@@ -535,6 +542,7 @@ def main():
         ctx.enable_timing(True)
         ctx.timing(reset=True)
         ctx.launches(reset=True)
+        clocks.wait_first()
         barrier()
         clocks.mark()
         ev0.record()

@@ -270,10 +270,9 @@ __global__ void __launch_bounds__(32) sqk_stats3_kernel(const Stats3Args A)
         if (inext < a.n_reads) nx = s2_describe(a, inext, alloc_lo, alloc_hi, A.buf_bytes);   // (its loads overlap the wait)
         bool staged_next = false;
         auto stage_next = [&]() {
-            if (!staged_next && inext < a.n_reads) {
-                __syncwarp();                                   // every lane is done with the staged samples
-                s3_stage(a, nx, bufs, bar);
-            }
+            __syncwarp();                                       // every lane is done with the staged samples (and, for
+                                                                // the callers that rely on it, with its shared stores)
+            if (!staged_next && inext < a.n_reads) s3_stage(a, nx, bufs, bar);
             staged_next = true;
         };
         if (rd.units > 0 && rd.tma) {

@@ -6,6 +6,7 @@ import socket
 import subprocess
 import sys
 import textwrap
+import time
 
 import pytest
 
@@ -41,6 +42,7 @@ WORKER = textwrap.dedent("""
         torch.cuda.synchronize()
         assert full.shape == one.shape and torch.equal(full, one), "sharded result differs from single-GPU result"
     dist.barrier()
+    print("rank", rank, "all-gather part done", flush=True)
 
     # ---- the same through PeerGather: the producing kernels store every record into every rank's buffer (P2P) ----
     from squigglekit_b200.dist import PeerGather
@@ -57,6 +59,7 @@ WORKER = textwrap.dedent("""
     one, _ = ctx.motifseq(dsig, torch.from_numpy(off[:n_even + 1].copy()).cuda(), motif, scale="zscale", max_read_len=2048)
     torch.cuda.synchronize()
     assert torch.equal(gathered, one), f"rank {rank}: records gathered over P2P differ from the single-GPU result"
+    print("rank", rank, "P2P part done", flush=True)
     # single-pass plan and a medmad run publish through the generic kernel / status records
     ctx.set_dtw_plan("single_pass")
     out = pg.local_buffer()
@@ -71,8 +74,8 @@ WORKER = textwrap.dedent("""
     torch.cuda.synchronize()
     assert torch.equal(got, one), f"rank {rank}: single-pass / medmad records gathered over P2P differ"
     dist.barrier()
+    print("rank", rank, "ok", flush=True)
     dist.destroy_process_group()
-    print("rank", rank, "ok")
 """)
 
 
@@ -90,7 +93,19 @@ def test_two_rank_shards_equal_single_gpu(tmp_path):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), SQK_ROOT=ROOT)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    # one deadline for both ranks; a rank that outlives it is killed and both outputs are shown (a rank that fails early
+    # leaves its peer waiting in a collective or on a P2P flag, so the interesting output is usually the OTHER rank's)
+    deadline = time.monotonic() + 240
+    outs, timed_out = [], []
+    for rank, p in enumerate(procs):
+        try:
+            outs.append(p.communicate(timeout=max(1.0, deadline - time.monotonic()))[0])
+        except subprocess.TimeoutExpired:
+            p.kill()
+            outs.append(p.communicate()[0])
+            timed_out.append(rank)
+    report = "\n".join(f"---- rank {r} (exit {p.returncode}) ----\n{o[-3000:]}" for r, (p, o) in enumerate(zip(procs, outs)))
+    assert not timed_out, f"rank(s) {timed_out} still running after 240 s\n{report}"
     for rank, (p, out) in enumerate(zip(procs, outs)):
-        assert p.returncode == 0, out[-3000:]
-        assert f"rank {rank} ok" in out
+        assert p.returncode == 0, report
+        assert f"rank {rank} ok" in out, report
