@@ -73,6 +73,7 @@ WORKER = textwrap.dedent("""
     ctx.set_dtw_plan("auto")
     torch.cuda.synchronize()
     assert torch.equal(got, one), f"rank {rank}: single-pass / medmad records gathered over P2P differ"
+    ctx.close()                                            # (as bench.py does: library context gone before the process group)
     dist.barrier()
     print("rank", rank, "ok", flush=True)
     dist.destroy_process_group()
