@@ -269,6 +269,12 @@ SQK_API int64_t sqk_tsv_format_segs(const char *heads, int64_t n_reads, const in
                                     const unsigned char *keep, int n_threads, char *out, int64_t cap);
 SQK_API int64_t sqk_tsv_format(const int16_t *samples, const int64_t *offsets, int64_t n_reads, const char *heads,
                                const int64_t *head_offsets, int n_threads, char *out, int64_t cap);
+/* The score columns of those rows (MotifSeq.py:441-445) on the host, without scipy: Z = (dist - mod_mean) / mod_stdev,
+ * p = scipy.stats.norm.cdf(Z) bit for bit (its ndtr: the Cephes algorithm and tables, libm's exp), hit_P = (1 - p) * 100, for
+ * hits [n_reads][n_models]; mod_mean / mod_stdev per model.  sqk_ndtr is the cdf alone. */
+SQK_API void sqk_score_hits(const void *hits, int64_t n_reads, int n_models, const double *mod_mean, const double *mod_stdev,
+                            int n_threads, double *zs, double *ps, double *hps);
+SQK_API void sqk_ndtr(const double *z, int64_t n, double *out);
 
 /* ---------------------------------------------------------------------------------------
  * Instrumentation (bench.py): per-kernel device time measured with cudaEvents recorded on the

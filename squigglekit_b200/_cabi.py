@@ -62,7 +62,7 @@ EXPORTS = [
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
     "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters", "sqk_ctx_get_plan_counters_ex",
     "sqk_ctx_get_launches", "sqk_ctx_set_stats_generation", "sqk_device_alloc", "sqk_device_free", "sqk_ipc_export", "sqk_ipc_open",
-    "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
+    "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs", "sqk_score_hits", "sqk_ndtr", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
 ]
 
 _lib = None
@@ -125,8 +125,13 @@ def lib() -> C.CDLL:
     L.sqk_tsv_format_rows.restype = i64
     L.sqk_tsv_format_segs.argtypes = [vp, i64, vp, vp, C.c_int, vp, C.c_int, vp, i64]
     L.sqk_tsv_format_segs.restype = i64
+    L.sqk_score_hits.argtypes = [vp, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    L.sqk_score_hits.restype = None
+    L.sqk_ndtr.argtypes = [vp, i64, vp]
+    L.sqk_ndtr.restype = None
     for name in EXPORTS:
-        if name not in ("sqk_version", "sqk_last_error", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs"):
+        if name not in ("sqk_version", "sqk_last_error", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs",
+                        "sqk_score_hits", "sqk_ndtr"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -71,11 +71,11 @@ def build_parser():
 
 def format_row(fast5, read_id, name, start, end, dist, m, b, std, L, extract=None):
     """The row get_region_multi prints (MotifSeq.py:441-449), same expressions, same formatting."""
-    import scipy.stats as st
+    from .tsv import ndtr                   # scipy.stats.norm.cdf bit for bit (scipy's ndtr restated in libsqk), without the import
     mod_mean = (m * L) + b
     mod_stdev = mod_mean * std
     Z = (dist - mod_mean) / mod_stdev
-    p_value = st.norm.cdf(Z)
+    p_value = ndtr(np.float64(Z))[()]       # numpy scalar, as norm.cdf returns
     hit_P = (1 - p_value) * 100
     cols = [fast5, read_id, name, start, end, end - start, dist, mod_mean, mod_stdev, Z, p_value, hit_P]
     if extract is not None:
@@ -85,9 +85,9 @@ def format_row(fast5, read_id, name, start, end, dist, m, b, std, L, extract=Non
 
 def format_rows(heads, names, hits, m, b, std, L):
     """The same rows for a whole batch: the per-model constants once, Z / p-value / probability as arrays (the same
-    IEEE operations and the same scipy ndtr as the scalar expressions), one join per row.  heads: [(fast5, readID)];
+    IEEE operations and scipy's ndtr, restated in libsqk, as the scalar expressions), one join per row.  heads: [(fast5, readID)];
     hits: structured [n_reads, n_models].  Reads with a status hit (start < 0) are skipped: -> (rows, skipped indices)."""
-    from scipy.special import ndtr          # what scipy.stats.norm.cdf evaluates (scipy/stats/_continuous_distns.py: _norm_cdf)
+    from .tsv import ndtr                   # scipy.special.ndtr bit for bit (what scipy.stats.norm.cdf evaluates), without the import
     rows, skipped = [], []
     n = len(heads)
     cols = []
@@ -113,18 +113,15 @@ def format_rows(heads, names, hits, m, b, std, L):
 def format_rows_bytes(heads_bytes, names, hits, m, b, std, L):
     """format_rows for a batch whose head columns are still text (tsv.Batch.heads_bytes): the per-model constants and the
     score arrays are computed here exactly as above, the text is written by libsqk.  -> (bytes, skipped [(read, code)])."""
-    from scipy.special import ndtr
     from . import tsv
-    consts, zs, ps, hps = [], [], [], []
+    consts, means, stdevs = [], [], []
     for c, name in enumerate(names):
         mod_mean = (m * L[c]) + b
         mod_stdev = mod_mean * std
-        dist = hits["dist"][:, c].astype(np.float64)
-        Z = (dist - mod_mean) / mod_stdev
-        p_value = ndtr(Z)
         consts.append("{}\t{}".format(mod_mean, mod_stdev))
-        zs.append(Z); ps.append(p_value); hps.append((1 - p_value) * 100)
-    text = tsv.format_hit_rows(heads_bytes, hits, names, consts, np.stack(zs, axis=1), np.stack(ps, axis=1), np.stack(hps, axis=1))
+        means.append(mod_mean); stdevs.append(mod_stdev)
+    zs, ps, hps = tsv.score_hits(hits, means, stdevs)      # (dist - mod_mean) / mod_stdev, norm.cdf, (1 - p) * 100
+    text = tsv.format_hit_rows(heads_bytes, hits, names, consts, zs, ps, hps)
     bad = np.argwhere(hits["start"] < 0)
     return text, [(int(r), int(hits["start"][r, c])) for r, c in bad]
 

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <charconv>
 #include <vector>
 
 #ifdef _OPENMP
@@ -52,13 +53,32 @@ extern "C" void sqk_parallel_memcpy(void *dst, const void *src, size_t bytes, in
     }
 }
 
-// parse one line's signal part [p, e) into out[0..n_fields); returns the status bits
-static int parse_fields_i16(const char *p, const char *e, int16_t *out, int64_t n_fields)
+// parse one line's signal part [p, e) into out[0..n_fields); returns the status bits.  `sentinel`: the byte at e can be read
+// and is not a digit (a newline: every line but an unterminated last one) -- the digit loop of the common case (a plain
+// non-negative number followed by a tab or the end of the line) then needs no bounds test.
+static int parse_fields_i16(const char *p, const char *e, int16_t *out, int64_t n_fields, bool sentinel)
 {
     int status = 0;
-    bool any_nonzero = false;
+    unsigned any_nonzero = 0;
     int64_t k = 0;
     while (p <= e && k < n_fields) {
+        if (sentinel && p < e) {
+            const unsigned char *q = (const unsigned char *)p;
+            unsigned v = (unsigned)*q - '0';
+            if (v <= 9u) {
+                unsigned d;
+                q++;
+                while ((d = (unsigned)*q - '0') <= 9u) { v = v * 10u + d; q++; }   // (stops at e at the latest)
+                const int nd = (int)((const char *)q - p);
+                if (nd <= 5 && v <= 32767u && (*q == '\t' || (const char *)q == e)) {
+                    out[k++] = (int16_t)v;
+                    any_nonzero |= v;
+                    p = (const char *)q + 1;
+                    continue;
+                }
+            }
+        }
+        // everything else: signs, CRLF, junk, out-of-range values, the unterminated last line
         const char *q = p;
         bool neg = false;
         if (q < e && (*q == '-' || *q == '+')) { neg = *q == '-'; q++; }
@@ -78,13 +98,34 @@ static int parse_fields_i16(const char *p, const char *e, int16_t *out, int64_t 
             if (neg) v = -v;
             if (v < -32768 || v > 32767) { status |= SQK_TSV_NOT_INT16; out[k] = 0; }
             else out[k] = (int16_t)v;
-            any_nonzero |= v != 0;
+            any_nonzero |= (unsigned)(v != 0);
         }
         k++;
         p = q + 1;
     }
     if (!(status & SQK_TSV_NOT_INT16) && !any_nonzero) status |= SQK_TSV_ALL_ZERO;
     return status;
+}
+
+// positions of the newlines in text[lo, hi), in order, found by all threads (each a contiguous piece)
+static void find_newlines(const char *text, int64_t lo, int64_t hi, int nt, std::vector<int64_t> &out)
+{
+    if (hi <= lo) return;
+    if (nt > 1 && hi - lo < (1 << 20)) nt = 1;
+    std::vector<std::vector<int64_t>> found((size_t)nt);
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+    for (int t = 0; t < nt; t++) {
+        const int64_t a = lo + (hi - lo) * t / nt, b = lo + (hi - lo) * (t + 1) / nt;
+        std::vector<int64_t> &v = found[(size_t)t];
+        const char *p = text + a, *e = text + b;
+        while (p < e) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) break;
+            v.push_back(nl - text);
+            p = nl + 1;
+        }
+    }
+    for (int t = 0; t < nt; t++) out.insert(out.end(), found[(size_t)t].begin(), found[(size_t)t].end());
 }
 
 extern "C" {
@@ -96,25 +137,45 @@ int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int start_col
     if (!text || !samples || !offsets || !line_begin || !sig_begin || !status || !n_lines_out || !consumed_out) return SQK_ERR_ARG;
     if (n_bytes < 0 || max_lines < 1 || start_col < 0) return SQK_ERR_ARG;
     // ---- 1. cut into lines, find where the signal columns start ------------------------------------------------------
-    std::vector<int64_t> line_end;
-    line_end.reserve((size_t)std::min<int64_t>(max_lines, 1 << 20));
-    int64_t pos = 0, n = 0;
-    while (pos < n_bytes && n < max_lines) {
-        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(n_bytes - pos));
-        int64_t end;
-        if (nl) end = nl - text;
-        else if (is_final) end = n_bytes;
-        else break;                                             // incomplete last line: the caller brings it back
-        line_begin[n] = pos;
-        line_end.push_back(end);
-        pos = nl ? end + 1 : end;
-        n++;
-    }
+    // The newlines of a window of the text sized for max_lines lines like the first one are found by all threads; the
+    // window grows while it holds fewer lines than asked for and there is text left.
 #ifdef _OPENMP
     const int nt = host_threads(n_threads);
 #else
     const int nt = 1; (void)n_threads;
 #endif
+    std::vector<int64_t> nlpos;
+    {
+        const char *first = n_bytes > 0 ? (const char *)memchr(text, '\n', (size_t)n_bytes) : nullptr;
+        const int64_t l1 = first ? (first - text) + 1 : n_bytes;
+        const double want = (double)l1 * (double)max_lines * 1.125 + 65536.0;
+        const int64_t step = want > 4e18 ? n_bytes : std::max<int64_t>((int64_t)want, 1 << 20);
+        int64_t scanned = 0;
+        while (scanned < n_bytes && (int64_t)nlpos.size() < max_lines) {
+            const int64_t hi = (n_bytes - scanned <= step) ? n_bytes : scanned + (scanned == 0 ? step : std::max<int64_t>(step / 4, 1 << 20));
+            find_newlines(text, scanned, hi, nt, nlpos);
+            scanned = hi;
+        }
+    }
+    std::vector<int64_t> line_end;
+    int64_t pos = 0, n = 0;
+    {
+        const int64_t n_nl = std::min<int64_t>((int64_t)nlpos.size(), max_lines);
+        line_end.resize((size_t)n_nl);
+        for (int64_t i = 0; i < n_nl; i++) {
+            line_begin[i] = pos;
+            line_end[(size_t)i] = nlpos[(size_t)i];
+            pos = nlpos[(size_t)i] + 1;
+        }
+        n = n_nl;
+        if (n < max_lines && (int64_t)nlpos.size() <= n && pos < n_bytes && is_final) {   // unterminated last line
+            line_begin[n] = pos;
+            line_end.push_back(n_bytes);
+            pos = n_bytes;
+            n++;
+        }
+        // (not final: an incomplete last line stays where it is -- the caller brings it back)
+    }
     std::vector<int64_t> n_fields((size_t)n);
 #pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t i = 0; i < n; i++) {
@@ -151,7 +212,8 @@ int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int start_col
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
     for (int64_t i = 0; i < used; i++) {
         if (status[i] & SQK_TSV_NO_SIGNAL) continue;
-        status[i] |= parse_fields_i16(text + sig_begin[i], text + line_end[(size_t)i], samples + offsets[i], n_fields[(size_t)i]);
+        status[i] |= parse_fields_i16(text + sig_begin[i], text + line_end[(size_t)i], samples + offsets[i], n_fields[(size_t)i],
+                                      /*sentinel=*/line_end[(size_t)i] < n_bytes);
     }
     line_begin[used] = used < n ? line_begin[used] : pos;
     *n_lines_out = used;
@@ -188,13 +250,11 @@ int64_t sqk_tsv_heads(const char *text, const int64_t *line_begin, const int64_t
     return need;
 }
 
-// Python's repr() of a float (= str() of a numpy float64): the shortest digit string that reads back as the same double,
-// fixed notation with at least ".0" when 1e-4 <= |x| < 1e16, otherwise d.ddde+XX with at least two exponent digits
-// (CPython: PyOS_double_to_string(x, 'r', 0, Py_DTSF_ADD_DOT_0), float_repr_style "short").  The shortest string has at
-// most 17 significant digits.  If it has <= 15, the correctly rounded 15-digit decimal IS that string padded with zeros
-// (a normal double lies within 1.2e-16 relative of it, less than half a unit of the 15th digit), so: print 15 digits, read
-// back, strip zeros; else the correctly rounded 16-digit decimal if it reads back (the closest of the 16-digit candidates,
-// which is the one repr picks), else the correctly rounded 17-digit one.  Returns the length written; buf needs 32 bytes.
+// Python's repr() of a float (= str() of a numpy float64): the shortest digit string that reads back as the same double
+// (the closest to it among the shortest), fixed notation with at least ".0" when 1e-4 <= |x| < 1e16, otherwise d.ddde+XX
+// with at least two exponent digits (CPython: PyOS_double_to_string(x, 'r', 0, Py_DTSF_ADD_DOT_0), float_repr_style
+// "short").  std::to_chars gives exactly those digits (shortest round trip); only the layout is Python's.  Returns the
+// length written; buf needs 32 bytes.  tests/test_host.py compares with repr() on ~10^6 doubles of every magnitude.
 static int fmt_repr(double x, char *buf)
 {
     if (x != x) { memcpy(buf, "nan", 3); return 3; }
@@ -203,14 +263,10 @@ static int fmt_repr(double x, char *buf)
     if (signbit(x)) { *w++ = '-'; x = -x; }
     if (x == 0.0) { memcpy(w, "0.0", 3); return (int)(w - buf) + 3; }
     char e[40];
-    if (x < 2.3e-308) {                                       // subnormal: few significant bits, try every length
-        for (int p = 0; p <= 16; p++) { snprintf(e, sizeof(e), "%.*e", p, x); if (strtod(e, nullptr) == x) break; }
-    } else {
-        snprintf(e, sizeof(e), "%.14e", x);                   // d.dddddddddddddde+XX
-        if (strtod(e, nullptr) != x) {
-            snprintf(e, sizeof(e), "%.15e", x);
-            if (strtod(e, nullptr) != x) snprintf(e, sizeof(e), "%.16e", x);
-        }
+    {
+        // shortest digits that read back as x, closest to x among the shortest (what repr prints), in d.ddde+XX form
+        const std::to_chars_result tr = std::to_chars(e, e + sizeof(e) - 1, x, std::chars_format::scientific);
+        *tr.ptr = 0;
     }
     char *ep = strchr(e, 'e');
     const int exp10 = atoi(ep + 1);
@@ -253,6 +309,88 @@ static int fmt_int(int v, char *buf)
     return n;
 }
 
+// ---- the score columns of a MotifSeq row (MotifSeq.py:441-445) ----------------------------------------------------------
+// Z = (dist - mod_mean) / mod_stdev; p = scipy.stats.norm.cdf(Z); hit_P = (1 - p) * 100.  scipy evaluates norm.cdf with
+// its ndtr (scipy/special: the Cephes ndtr.c algorithm, now in its xsf headers): x = Z / sqrt(2), 0.5 + 0.5 erf(x) for
+// |x| < 1, else 0.5 erfc(|x|) reflected; erf and erfc are Cephes' rational approximations (coefficient tables P/Q for
+// 1 <= x < 8, R/S beyond, T/U for erf below 1), not libm's.  Restated here so that the command line does not have to import
+// scipy (0.35-0.75 s per process); tests/test_tsv.py checks bit equality with scipy.special.ndtr on millions of values.
+// exp() is libm's, as in scipy's build; no FMA contraction (the Makefile passes -ffp-contract=off for this file).
+static const double ND_P[] = {2.46196981473530512524E-10, 5.64189564831068821977E-1, 7.46321056442269912687E0,
+                              4.86371970985681366614E1, 1.96520832956077098242E2, 5.26445194995477358631E2,
+                              9.34528527171957607540E2, 1.02755188689515710272E3, 5.57535335369399327526E2};
+static const double ND_Q[] = {1.32281951154744992508E1, 8.67072140885989742329E1, 3.54937778887819891062E2,
+                              9.75708501743205489753E2, 1.82390916687909736289E3, 2.24633760818710981792E3,
+                              1.65666309194161350182E3, 5.57535340817727675546E2};
+static const double ND_R[] = {5.64189583547755073984E-1, 1.27536670759978104416E0, 5.01905042251180477414E0,
+                              6.16021097993053585195E0, 7.40974269950448939160E0, 2.97886665372100240670E0};
+static const double ND_S[] = {2.26052863220117276590E0, 9.39603524938001434673E0, 1.20489539808096656605E1,
+                              1.70814450747565897222E1, 9.60896809063285878198E0, 3.36907645100081516050E0};
+static const double ND_T[] = {9.60497373987051638749E0, 9.00260197203842689217E1, 2.23200534594684319226E3,
+                              7.00332514112805075473E3, 5.55923013010394962768E4};
+static const double ND_U[] = {3.35617141647503099647E1, 5.21357949780152679795E2, 4.59432382970980127987E3,
+                              2.26290000613890934246E4, 4.92673942608635921086E4};
+static inline double nd_polevl(double x, const double *c, int n) { double a = c[0]; for (int i = 1; i <= n; i++) a = a * x + c[i]; return a; }
+static inline double nd_p1evl(double x, const double *c, int n) { double a = x + c[0]; for (int i = 1; i < n; i++) a = a * x + c[i]; return a; }
+static double nd_erf(double x);
+static double nd_erfc(double a)
+{
+    if (a != a) return a;
+    const double x = a < 0.0 ? -a : a;
+    if (x < 1.0) return 1.0 - nd_erf(a);
+    double z = -a * a;
+    if (z < -7.09782712893383996843E2) return a < 0 ? 2.0 : 0.0;      // exp underflows
+    z = exp(z);
+    double p, q;
+    if (x < 8.0) { p = nd_polevl(x, ND_P, 8); q = nd_p1evl(x, ND_Q, 8); }
+    else { p = nd_polevl(x, ND_R, 5); q = nd_p1evl(x, ND_S, 6); }
+    double y = (z * p) / q;
+    if (a < 0) y = 2.0 - y;
+    if (y == 0.0) return a < 0 ? 2.0 : 0.0;
+    return y;
+}
+static double nd_erf(double x)
+{
+    if (x != x) return x;
+    if (x < 0.0) return -nd_erf(-x);
+    if (x > 1.0) return 1.0 - nd_erfc(x);
+    const double z = x * x;
+    return x * nd_polevl(z, ND_T, 4) / nd_p1evl(z, ND_U, 5);
+}
+static double nd_ndtr(double a)
+{
+    if (a != a) return a;
+    const double x = a * 7.07106781186547524401E-1, z = fabs(x);
+    if (z < 1.0) return 0.5 + 0.5 * nd_erf(x);
+    const double y = 0.5 * nd_erfc(z);
+    return x > 0 ? 1.0 - y : y;
+}
+
+void sqk_ndtr(const double *z, int64_t n, double *out)
+{
+    if (!z || !out) return;
+    for (int64_t i = 0; i < n; i++) out[i] = nd_ndtr(z[i]);
+}
+
+// Z-score, p-value and hit probability of every (read, model) record: hits [n_reads][n_models] sqk_hit, mod_mean / mod_stdev
+// per model; zs / ps / hps [n_reads][n_models].
+void sqk_score_hits(const void *hits_v, int64_t n_reads, int n_models, const double *mod_mean, const double *mod_stdev,
+                    int n_threads, double *zs, double *ps, double *hps)
+{
+    if (!hits_v || !mod_mean || !mod_stdev || !zs || !ps || !hps || n_reads <= 0 || n_models <= 0) return;
+    const sqk_hit *hits = (const sqk_hit *)hits_v;
+    const int nt = host_threads(n_threads);
+    (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t r = 0; r < n_reads; r++)
+        for (int m = 0; m < n_models; m++) {
+            const int64_t i = r * n_models + m;
+            const double Z = (hits[i].dist - mod_mean[m]) / mod_stdev[m];
+            const double p = nd_ndtr(Z);
+            zs[i] = Z; ps[i] = p; hps[i] = (1.0 - p) * 100.0;
+        }
+}
+
 // The rows get_region_multi prints (MotifSeq.py:441-449) for a batch, as text:
 //   head <TAB> name <TAB> start <TAB> end <TAB> end-start <TAB> dist <TAB> consts <TAB> Z <TAB> p <TAB> hit_P <NL>
 // heads: "fast5 <TAB> readID <NL>" per read (sqk_tsv_heads); names / consts ("mod_mean <TAB> mod_stdev" already as text):
@@ -284,7 +422,8 @@ int64_t sqk_tsv_format_rows(const char *heads, int64_t n_reads, const void *hits
     }
     if (!out || at[(size_t)n_reads] > cap) return -at[(size_t)n_reads];
     std::vector<int64_t> len((size_t)n_reads);
-    const int nt = host_threads(n_threads);
+    // (a row costs ~0.3 us: a team of threads only pays for itself on batches of several hundred thousand rows)
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(n_threads), n_reads * n_models / 131072));
 #pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t r = 0; r < n_reads; r++) {
         char *w = out + at[(size_t)r];
@@ -332,7 +471,7 @@ int64_t sqk_tsv_format_segs(const char *heads, int64_t n_reads, const int32_t *s
         at[(size_t)r + 1] = at[(size_t)r] + (keep[r] ? (hb[(size_t)r + 1] - hb[(size_t)r]) + 2 + 24ll * (n > 0 ? n : 0) : 0);
     }
     if (!out || at[(size_t)n_reads] > cap) return -at[(size_t)n_reads];
-    const int nt = host_threads(n_threads);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(n_threads), n_reads / 131072));
 #pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t r = 0; r < n_reads; r++) {
         char *w = out + at[(size_t)r];

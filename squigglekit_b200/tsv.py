@@ -20,6 +20,7 @@ import numpy as np
 from . import _cabi
 
 NO_SIGNAL, NOT_INT16, ALL_ZERO = 1, 2, 4
+DEFAULT_PINNED = True       # Reader(pinned=None): page-locked sample buffer (the CPU test-suite, which has no CUDA runtime, clears this)
 
 
 @dataclass
@@ -66,13 +67,28 @@ class Batch:
         return self.signals[int(self.offsets[i]):int(self.offsets[i + 1])]
 
 
+class _Slot:
+    """One batch's worth of parse output: a slice of the (pinned) sample buffer and the per-line arrays."""
+
+    def __init__(self, samples: np.ndarray, max_lines: int):
+        self.samples = samples
+        self.offsets = np.zeros(max_lines + 1, dtype=np.int64)
+        self.line_begin = np.zeros(max_lines + 1, dtype=np.int64)
+        self.sig_begin = np.zeros(max_lines, dtype=np.int64)
+        self.status = np.zeros(max_lines, dtype=np.int32)
+
+
 class Reader:
     """Iterate over a SquigglePull TSV as parsed batches of at most ``max_lines`` lines / ``max_samples`` samples.  A
     plain file is memory-mapped and parsed in place (no copy of the text is ever made); a .gz file is streamed through a
-    buffer.  The sample buffer is pinned when ``pinned`` (needs the CUDA runtime, i.e. a GPU box)."""
+    buffer.  The sample buffer is pinned when ``pinned`` (needs the CUDA runtime, i.e. a GPU box).
+
+    ``prefetch`` (plain files): the sample buffer is cut into two slots of ``max_samples // 2`` and a helper thread parses
+    the next batch into the free slot while the caller works on the current one (its GPU call, its row formatting) --
+    ``sqk_tsv_parse`` runs outside the GIL.  A batch is valid until the iterator is advanced, as without prefetch."""
 
     def __init__(self, path: str, start_col: int, max_lines: int = 16384, max_samples: int = 96 << 20,
-                 block_bytes: int = 128 << 20, pinned: bool = True, n_threads: int = 0):
+                 block_bytes: int = 128 << 20, pinned=None, n_threads: int = 0, prefetch: bool = True):
         import mmap
         import os
         self.lib = _cabi.lib()
@@ -93,17 +109,18 @@ class Reader:
                     pass
                 self.mm_arr = np.frombuffer(self.mm, dtype=np.uint8)
             self.size = size
+        self.prefetch = bool(prefetch) and self.fh is None and self.max_samples >= 16
+        n_slots = 2 if self.prefetch else 1
+        self.slot_samples = (self.max_samples // n_slots) & ~7 if n_slots > 1 else self.max_samples
         self._pinned = None
-        if pinned:
+        if DEFAULT_PINNED if pinned is None else pinned:
             from .core import pinned_empty
             self._pinned = pinned_empty(self.max_samples, np.int16)
-            self.samples = self._pinned
+            big = self._pinned
         else:
-            self.samples = np.empty(self.max_samples, dtype=np.int16)
-        self.offsets = np.zeros(self.max_lines + 1, dtype=np.int64)
-        self.line_begin = np.zeros(self.max_lines + 1, dtype=np.int64)
-        self.sig_begin = np.zeros(self.max_lines, dtype=np.int64)
-        self.status = np.zeros(self.max_lines, dtype=np.int32)
+            big = np.empty(self.max_samples, dtype=np.int16)
+        self._slots = [_Slot(big[k * self.slot_samples:(k + 1) * self.slot_samples], self.max_lines) for k in range(n_slots)]
+        self.samples = self._slots[0].samples
         self.buf = bytearray()
         self.pos = 0
         self.eof = False
@@ -132,21 +149,68 @@ class Reader:
     def __exit__(self, *a):
         self.close()
 
-    def _parse(self, addr, avail, final):
+    def _parse(self, addr, avail, final, slot):
         n_lines, consumed = C.c_int64(0), C.c_int64(0)
-        rc = self.lib.sqk_tsv_parse(addr, avail, int(final), self.start_col, self.max_lines, self.max_samples,
-                                    self.n_threads, self.samples.ctypes.data, self.offsets.ctypes.data,
-                                    self.line_begin.ctypes.data, self.sig_begin.ctypes.data, self.status.ctypes.data,
+        rc = self.lib.sqk_tsv_parse(addr, avail, int(final), self.start_col, self.max_lines, slot.samples.size,
+                                    self.n_threads, slot.samples.ctypes.data, slot.offsets.ctypes.data,
+                                    slot.line_begin.ctypes.data, slot.sig_begin.ctypes.data, slot.status.ctypes.data,
                                     C.byref(n_lines), C.byref(consumed))
         if rc == _cabi.SQK_ERR_NOMEM:
-            raise ValueError("a line of the signal file holds more samples than the batch buffer (%d)" % self.max_samples)
+            raise ValueError("a line of the signal file holds more samples than the batch buffer (%d)" % slot.samples.size)
         if rc != 0:
             raise RuntimeError("sqk_tsv_parse failed (%d)" % rc)
         return int(n_lines.value), int(consumed.value)
 
-    def _batch(self, text, base, n):
-        return Batch(text, base, self.line_begin[:n + 1].copy(), self.sig_begin[:n].copy(), self.offsets[:n + 1].copy(),
-                     self.status[:n].copy(), self.samples, n)
+    def _batch(self, text, base, n, slot):
+        return Batch(text, base, slot.line_begin[:n + 1].copy(), slot.sig_begin[:n].copy(), slot.offsets[:n + 1].copy(),
+                     slot.status[:n].copy(), slot.samples, n)
+
+    def _iter_mmap_prefetch(self):
+        """The memory-mapped file with a helper thread one batch ahead (two slots)."""
+        import queue
+        import threading
+        base = self.mm_arr.ctypes.data
+        done, free = queue.Queue(), queue.Queue()
+        for k in range(len(self._slots)):
+            free.put(k)
+        stop = threading.Event()
+
+        def work():
+            pos = 0
+            try:
+                while pos < self.size and not stop.is_set():
+                    k = free.get()
+                    if k is None:
+                        break
+                    n, used = self._parse(base + pos, self.size - pos, True, self._slots[k])
+                    if n == 0:
+                        break
+                    done.put((k, pos, n, used))
+                    pos += used
+                done.put(None)
+            except BaseException as e:                      # handed to the consumer, raised there
+                done.put(e)
+
+        t = threading.Thread(target=work, name="sqk-tsv-prefetch", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = done.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                k, pos, n, used = item
+                mv = memoryview(self.mm)[pos:pos + used]
+                try:
+                    yield self._batch(mv, base + pos, n, self._slots[k])
+                finally:
+                    mv.release()
+                free.put(k)                                 # the caller is done with that batch: its slot may be refilled
+        finally:
+            stop.set()
+            free.put(None)
+            t.join()
 
     def _fill(self):
         if self.pos:
@@ -162,14 +226,17 @@ class Reader:
         if self.fh is None:                                      # memory-mapped plain file
             if self.mm is None:
                 return
-            pos, base = 0, self.mm_arr.ctypes.data
+            if self.prefetch:
+                yield from self._iter_mmap_prefetch()
+                return
+            pos, base, slot = 0, self.mm_arr.ctypes.data, self._slots[0]
             while pos < self.size:
-                n, used = self._parse(base + pos, self.size - pos, True)
+                n, used = self._parse(base + pos, self.size - pos, True, slot)
                 if n == 0:
                     return
                 mv = memoryview(self.mm)[pos:pos + used]
                 try:
-                    yield self._batch(mv, base + pos, n)
+                    yield self._batch(mv, base + pos, n, slot)
                 finally:
                     mv.release()
                 pos += used
@@ -184,14 +251,14 @@ class Reader:
                 continue
             view = (C.c_char * avail).from_buffer(self.buf, self.pos)
             try:
-                n, used = self._parse(C.addressof(view), avail, self.eof)
+                n, used = self._parse(C.addressof(view), avail, self.eof, self._slots[0])
                 if n == 0:
                     if self.eof:
                         return
                 else:
                     mv = memoryview(self.buf)[self.pos:self.pos + used]
                     try:
-                        yield self._batch(mv, C.addressof(view), n)
+                        yield self._batch(mv, C.addressof(view), n, self._slots[0])
                     finally:
                         mv.release()
                     self.pos += used
@@ -225,6 +292,31 @@ def write_reads(fh, heads, signals, offsets, n_threads: int = 0):
     fh.write(format_reads(heads, signals, offsets, n_threads))
 
 
+def ndtr(z) -> np.ndarray:
+    """``scipy.special.ndtr`` (what ``scipy.stats.norm.cdf`` evaluates) bit for bit, from libsqk (``sqk_ndtr``): the command
+    lines do not import scipy."""
+    z = np.asarray(z, dtype=np.float64)
+    flat = np.ascontiguousarray(z).reshape(-1)
+    out = np.empty_like(flat)
+    _cabi.lib().sqk_ndtr(flat.ctypes.data, flat.size, out.ctypes.data)
+    return out.reshape(z.shape)             # (0-d in, 0-d out: index with [()] for the numpy scalar)
+
+
+def score_hits(hits: np.ndarray, mod_mean, mod_stdev, n_threads: int = 0):
+    """Z-score, p-value and hit probability (MotifSeq.py:443-445) of every record of ``hits`` [n_reads, n_models] for the
+    per-model ``mod_mean`` / ``mod_stdev`` -> three float64 arrays [n_reads, n_models] (``sqk_score_hits``)."""
+    hits = np.ascontiguousarray(hits)
+    n, m = hits.shape
+    mm = np.ascontiguousarray(mod_mean, dtype=np.float64)
+    ms = np.ascontiguousarray(mod_stdev, dtype=np.float64)
+    if mm.size != m or ms.size != m:
+        raise ValueError("one mod_mean / mod_stdev per model")
+    zs, ps, hps = (np.empty((n, m), dtype=np.float64) for _ in range(3))
+    _cabi.lib().sqk_score_hits(hits.ctypes.data, n, m, mm.ctypes.data, ms.ctypes.data, n_threads, zs.ctypes.data, ps.ctypes.data,
+                               hps.ctypes.data)
+    return zs, ps, hps
+
+
 def format_hit_rows(heads: bytes, hits: np.ndarray, names, consts, zs: np.ndarray, ps: np.ndarray, hps: np.ndarray,
                     n_threads: int = 0) -> bytes:
     """The rows get_region_multi prints (MotifSeq.py:441-449) for a batch, formatted by libsqk (``sqk_tsv_format_rows``):
@@ -241,12 +333,10 @@ def format_hit_rows(heads: bytes, hits: np.ndarray, names, consts, zs: np.ndarra
                                         n_threads, None, 0))
     if need <= 0:
         return b""
-    out = bytearray(need)
-    view = (C.c_char * need).from_buffer(out)
+    out = np.empty(need, dtype=np.uint8)                    # (an upper bound; not zero-filled, copied out once)
     got = int(lib.sqk_tsv_format_rows(heads, n, hits.ctypes.data, m, nb, cb, zs.ctypes.data, ps.ctypes.data, hps.ctypes.data,
-                                      n_threads, C.addressof(view), need))
-    del view
-    return bytes(out[:got])
+                                      n_threads, out.ctypes.data, need))
+    return out[:got].tobytes()
 
 
 def format_seg_rows(heads: bytes, segs: np.ndarray, n_segs: np.ndarray, keep: np.ndarray, n_threads: int = 0) -> bytes:

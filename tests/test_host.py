@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 import squigglekit_b200 as sqk
 from squigglekit_b200 import cli_motifseq, cli_segmenter, fast5
@@ -125,6 +126,23 @@ def test_vectorised_rows_equal_the_per_read_rows():
             want.append(cli_motifseq.format_row(heads[r][0], heads[r][1], name, int(h["start"]), int(h["end"]), h["dist"], 2.90, -9.6,
                                                 0.08468, L[c]))
     assert rows == want
+    # format_row itself against the reference's expressions with the real scipy (MotifSeq.py:441-449)
+    st = pytest.importorskip("scipy.stats")
+    k = 0
+    for r in range(n):
+        for c, name in enumerate(names):
+            h = hits[r, c]
+            if int(h["start"]) < 0:
+                continue
+            start, end, dist = int(h["start"]), int(h["end"]), h["dist"]
+            mod_mean = (2.90 * L[c]) + -9.6
+            mod_stdev = mod_mean * 0.08468
+            Z = (dist - mod_mean) / mod_stdev
+            p_value = st.norm.cdf(Z)
+            hit_P = (1 - p_value) * 100
+            ref = "\t".join("{}".format(x) for x in [heads[r][0], heads[r][1], name, start, end, end - start, dist, mod_mean, mod_stdev, Z, p_value, hit_P])
+            assert want[k] == ref
+            k += 1
     assert sorted(skipped) == [(7, -1), (9, -2)]
     # ... and so does the formatter in libsqk (floats as Python's repr writes them)
     hb = ("\n".join(f"{a}\t{b}" for a, b in heads) + "\n").encode()
