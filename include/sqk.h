@@ -337,8 +337,11 @@ SQK_API int sqk_ctx_set_stats_generation(sqk_ctx *ctx, int generation);
  *                 sqk_peer_signal(step)       -- after the step's kernels, stream-ordered
  *   to read:      sqk_peer_wait(step)         -- stream-ordered: returns (on the stream) once every rank signalled `step`
  *
- * Only device-mode sqk_motifseq publishes.  A buffer may be rewritten by a later step as soon as that step runs: the
- * caller rotates buffers (sqk_ctx_set_hit_peers per step) and reads a buffer before the ranks reuse it.
+ * Only device-mode sqk_motifseq publishes, and sqk_ctx_set_hit_peers arms ONE call: the next device-mode sqk_motifseq
+ * stores its records into the peers' buffers, calls after it do not until the peers are set again (a call that is not
+ * part of the exchange -- a comparison run, another batch -- must never write into a peer's memory).  A buffer may be
+ * rewritten by a later step as soon as that step runs: the caller rotates buffers (sqk_ctx_set_hit_peers per step) and
+ * reads a buffer before the ranks reuse it.
  * ------------------------------------------------------------------------------------- */
 SQK_API int sqk_device_alloc(sqk_ctx *ctx, uint64_t bytes, void **dev_ptr);     /* zero-filled; IPC-exportable */
 SQK_API int sqk_device_free(sqk_ctx *ctx, void *dev_ptr);
@@ -348,6 +351,10 @@ SQK_API int sqk_ipc_close(sqk_ctx *ctx, void *dev_ptr);
 /* peers[n_peers]: bases of the OTHER ranks' gathered buffers (device pointers valid on this GPU); record r of this rank
  * is stored at peers[p][(first_record + r) * n_models + m].  n_peers = 0 turns publication off. */
 SQK_API int sqk_ctx_set_hit_peers(sqk_ctx *ctx, void *const *peers, int n_peers, int64_t first_record);
+/* the same with the size of a gathered buffer in records: a call whose block [first_record, first_record + n_reads) does not
+ * fit is refused (SQK_ERR_ARG) instead of storing past the end of a peer's buffer */
+SQK_API int sqk_ctx_set_hit_peers_ex(sqk_ctx *ctx, void *const *peers, int n_peers, int64_t first_record,
+                                     int64_t capacity_records);
 /* flag_arrays[n_ranks]: every rank's flag array (uint64[16], zero-filled), the own one at index my_rank. */
 SQK_API int sqk_ctx_set_flag_peers(sqk_ctx *ctx, void *const *flag_arrays, int n_ranks, int my_rank);
 SQK_API int sqk_peer_signal(sqk_ctx *ctx, uint64_t value);

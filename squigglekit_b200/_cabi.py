@@ -62,7 +62,7 @@ EXPORTS = [
     "sqk_device_count", "sqk_ctx_device_props", "sqk_host_alloc", "sqk_host_free", "sqk_motifseq",
     "sqk_motifseq_trace", "sqk_segmenter", "sqk_segmenter_pa", "sqk_adapter", "sqk_motifseq_f64", "sqk_segmenter_f64", "sqk_ctx_enable_timing", "sqk_ctx_get_timing", "sqk_ctx_set_dtw_lanes", "sqk_ctx_set_chunk_samples", "sqk_ctx_set_dtw_plan", "sqk_ctx_get_plan_counters", "sqk_ctx_get_plan_counters_ex",
     "sqk_ctx_get_launches", "sqk_ctx_set_stats_generation", "sqk_device_alloc", "sqk_device_free", "sqk_ipc_export", "sqk_ipc_open",
-    "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs", "sqk_score_hits", "sqk_ndtr", "sqk_ctx_set_hit_peers", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
+    "sqk_ipc_close", "sqk_rollmean", "sqk_tsv_parse", "sqk_tsv_format", "sqk_tsv_heads", "sqk_tsv_format_rows", "sqk_tsv_format_segs", "sqk_score_hits", "sqk_ndtr", "sqk_ctx_set_hit_peers", "sqk_ctx_set_hit_peers_ex", "sqk_ctx_set_flag_peers", "sqk_peer_signal", "sqk_peer_wait",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
     L.sqk_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.sqk_ipc_close.argtypes = [vp, vp]
     L.sqk_ctx_set_hit_peers.argtypes = [vp, C.POINTER(vp), C.c_int, i64]
+    L.sqk_ctx_set_hit_peers_ex.argtypes = [vp, C.POINTER(vp), C.c_int, i64, i64]
     L.sqk_ctx_set_flag_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int]
     L.sqk_peer_signal.argtypes = [vp, C.c_uint64]
     L.sqk_peer_wait.argtypes = [vp, C.c_uint64]

@@ -183,9 +183,11 @@ class Context:
     def ipc_close(self, ptr: int):
         _cabi.check(self._lib.sqk_ipc_close(self._h, C.c_void_p(ptr)))
 
-    def set_hit_peers(self, peers, first_record: int = 0):
+    def set_hit_peers(self, peers, first_record: int = 0, capacity_records: int = 0):
+        """Arm the NEXT device-mode motifseq call to store its records into the peers' gathered buffers as well (P2P); calls
+        after it do not publish until this is called again.  capacity_records: size of a gathered buffer (bounds check)."""
         arr = (C.c_void_p * max(1, len(peers)))(*[C.c_void_p(p) for p in peers])
-        _cabi.check(self._lib.sqk_ctx_set_hit_peers(self._h, arr, len(peers), int(first_record)))
+        _cabi.check(self._lib.sqk_ctx_set_hit_peers_ex(self._h, arr, len(peers), int(first_record), int(capacity_records)))
 
     def set_flag_peers(self, flag_arrays, my_rank: int):
         arr = (C.c_void_p * max(1, len(flag_arrays)))(*[C.c_void_p(p) for p in flag_arrays])

@@ -187,6 +187,7 @@ struct sqk_ctx {
     // call that arrives on a different stream waits for it first
     PeerOut peers{};                  // multi-GPU publication targets of device-mode sqk_motifseq (sqk_ctx_set_hit_peers)
     int64_t peer_base = 0;            // first record of this rank in a gathered buffer
+    int64_t peer_cap = 0;             // records a gathered buffer holds (0 = not told: no bounds check)
     PeerFlags flags{};
     int64_t n_launches = 0;           // kernels launched (sqk_ctx_get_launches)
     cudaEvent_t dev_done = nullptr;
@@ -1434,12 +1435,12 @@ int sqk_ipc_close(sqk_ctx *c, void *p)
     return SQK_OK;
 }
 
-int sqk_ctx_set_hit_peers(sqk_ctx *c, void *const *peers, int n_peers, int64_t first_record)
+int sqk_ctx_set_hit_peers_ex(sqk_ctx *c, void *const *peers, int n_peers, int64_t first_record, int64_t capacity_records)
 {
     if (!c) return fail(SQK_ERR_ARG, "ctx is NULL");
     if (n_peers < 0 || n_peers > SQK_MAX_PEERS) return fail(SQK_ERR_ARG, "n_peers must be 0..%d", SQK_MAX_PEERS);
     if (n_peers > 0 && !peers) return fail(SQK_ERR_ARG, "peers is NULL");
-    if (first_record < 0) return fail(SQK_ERR_ARG, "first_record < 0");
+    if (first_record < 0 || capacity_records < 0) return fail(SQK_ERR_ARG, "first_record / capacity_records < 0");
     c->peers = PeerOut{};
     for (int p = 0; p < n_peers; p++) {
         if (!peers[p]) return fail(SQK_ERR_ARG, "peers[%d] is NULL", p);
@@ -1447,7 +1448,13 @@ int sqk_ctx_set_hit_peers(sqk_ctx *c, void *const *peers, int n_peers, int64_t f
     }
     c->peers.n = n_peers;
     c->peer_base = first_record;
+    c->peer_cap = capacity_records;
     return SQK_OK;
+}
+
+int sqk_ctx_set_hit_peers(sqk_ctx *c, void *const *peers, int n_peers, int64_t first_record)
+{
+    return sqk_ctx_set_hit_peers_ex(c, peers, n_peers, first_record, 0);
 }
 
 int sqk_ctx_set_flag_peers(sqk_ctx *c, void *const *flag_arrays, int n_ranks, int my_rank)
@@ -1520,8 +1527,17 @@ int sqk_motifseq(sqk_ctx *c, const int16_t *signals, const int64_t *offsets, int
         View v{signals, 1, 0, offsets, 0, n_reads, max_read_len};   // bounds resolved on the device from offsets
         // device mode: the caller's allocation bounds are unknown, so [offsets[0], offsets[n]) delimits what the
         // kernels may touch (resolve_bounds): 16-byte blocks sticking out of it are read sample by sample.
+        // Publication is armed for ONE call (sqk_ctx_set_hit_peers before every step): a later call that is not part of
+        // the exchange -- a check against a single-GPU run, another batch shape -- must not write into the peers' buffers.
+        const bool publish = c->peers.n > 0;
+        if (publish && c->peer_cap > 0 && c->peer_base + n_reads > c->peer_cap) {
+            c->peers.n = 0;
+            return fail(SQK_ERR_ARG, "publication: records [%lld, %lld) do not fit the peers' buffers of %lld records",
+                        (long long)c->peer_base, (long long)(c->peer_base + n_reads), (long long)c->peer_cap);
+        }
         const int rc = enqueue_motifseq(c, c->slot[0], st, v, (const double *)c->model.p, models, model_offsets, n_models, p, hits, n_kept,
-                                        /*publish=*/c->peers.n > 0);
+                                        publish);
+        c->peers.n = 0;
         TRY(dev_end(c, st));
         return rc;
     }

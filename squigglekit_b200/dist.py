@@ -151,7 +151,8 @@ class PeerGather:
 
     def local_buffer(self):
         k = self.i % self.depth
-        self.ctx.set_hit_peers(self.peer_bufs[k], first_record=self.rank * self.n_local)
+        self.ctx.set_hit_peers(self.peer_bufs[k], first_record=self.rank * self.n_local,
+                               capacity_records=self.world * self.n_local)       # arms the next motifseq call only
         return self.views[k][self.rank * self.n_local:(self.rank + 1) * self.n_local]
 
     def submit(self):

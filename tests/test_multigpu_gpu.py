@@ -45,6 +45,9 @@ WORKER = textwrap.dedent("""
     print("rank", rank, "all-gather part done", flush=True)
 
     # ---- the same through PeerGather: the producing kernels store every record into every rank's buffer (P2P) ----
+    # (local_buffer() arms ONE motifseq call; the comparison runs below, on the same context, must not publish -- an
+    # earlier version of the library left publication on, and rank 1's 1000-record comparison run stored past the end of
+    # rank 0's 1000-record buffer)
     from squigglekit_b200.dist import PeerGather
     n_even = 1000
     per = n_even // world
