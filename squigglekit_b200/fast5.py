@@ -4,10 +4,11 @@ process_fast5, MotifSeq.py:327-351 / segmenter.py:321-355; read_multi_fast5, seg
 h5py is not installed in the target image, so this is a small pure-Python reader for the subset of
 HDF5 that MinKNOW / ont_fast5_api files use: superblock v0-v1, version-1 object headers with
 continuation blocks, old-style groups (symbol-table B-trees + local heaps) and compact link
-messages, contiguous / compact / chunked datasets with the deflate and shuffle filters, fixed- and
-variable-length string attributes (global heap) and numeric scalar attributes.  VBZ-compressed
-signal (filter 32020) needs ONT's plugin and is reported as unsupported.  If h5py happens to be
-importable it is NOT used: one code path, tested here.
+messages, contiguous / compact / chunked datasets with the deflate, shuffle, fletcher32 and VBZ (ONT's
+filter 32020: zstd + StreamVByte + zig-zag delta, decoded in ``codecs.py`` -- the reference needs the
+`vbz` HDF5 plugin for those files, README.md:100-104) filters, fixed- and variable-length string
+attributes (global heap) and numeric scalar attributes.  If h5py happens to be importable it is NOT
+used: one code path, tested here.
 
 Host-side I/O only -- the samples it returns go to the GPU as int16.
 """
@@ -17,6 +18,8 @@ import struct
 import zlib
 
 import numpy as np
+
+from . import codecs
 
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
@@ -368,10 +371,7 @@ class Node:
         if len(ds.shape) != 1:
             raise Fast5Error("only 1-D chunked datasets are supported")
         for fid, _ in ds.filters:
-            if fid == 32020:
-                raise Fast5Error("VBZ-compressed signal (HDF5 filter 32020) needs ONT's vbz plugin; "
-                                 "convert with `compress_fast5 -c gzip` first")
-            if fid not in (1, 2, 3):
+            if fid not in (1, 2, 3, 32020):
                 raise Fast5Error(f"HDF5 filter {fid} not supported")
         out = np.zeros(ds.shape[0], dtype=ds.dtype)
         chunk_len = ds.layout[2][0]
@@ -389,6 +389,11 @@ class Node:
                     raw = a[:cnt * esize].reshape(esize, cnt).T.tobytes()
                 elif fid == 3:
                     raw = raw[:-4]
+                elif fid == 32020:                            # ONT's VBZ (zstd + StreamVByte + zig-zag delta), codecs.py
+                    try:
+                        raw = codecs.vbz_decode(raw, cd, esize)
+                    except codecs.CodecError as e:
+                        raise Fast5Error(f"VBZ chunk at {addr}: {e}") from e
             vals = np.frombuffer(raw, dtype=ds.dtype, count=min(chunk_len, len(raw) // esize))
             take = min(vals.size, ds.shape[0] - off)
             out[off:off + take] = vals[:take]
