@@ -71,11 +71,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
         self.t0 = self.t1 = None
 
     def __enter__(self):
+        if not self.enabled:                                     # (only the rank that prints the line samples its GPU)
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -534,7 +536,7 @@ def main():
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sustained = None
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
         for _ in range(args.warmup):
             gathered = step()
         pipe.drain()

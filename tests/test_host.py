@@ -197,3 +197,26 @@ def test_segmenter_rows_batched_equal_per_read(capsys):
                 cli_segmenter.emit_batch(args, cfg, hb, segs, nsegs, b)
                 assert a.getvalue() == b.getvalue() and a.getvalue().count("\n") > 50
     capsys.readouterr()
+
+
+def test_clock_sampler_without_nvidia_smi(monkeypatch):
+    """bench.py's clock sampler: no nvidia-smi (this container), a disabled sampler (ranks other than 0) and the wait for the
+    first sample all end quietly with an empty summary; rows that did arrive are digested."""
+    import time
+    import bench
+    monkeypatch.setenv("PATH", "/nonexistent")
+    for enabled in (True, False):
+        with bench.ClockSampler(0, enabled=enabled) as c:
+            t0 = time.perf_counter()
+            c.wait_first(timeout=5.0)
+            assert time.perf_counter() - t0 < 1.0
+            c.mark(); c.unmark()
+            assert c.summary() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    c = bench.ClockSampler(0)
+    now = time.perf_counter()
+    c.rows = [(now - 1.0, ["1965", "1965", "200.0", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"]),
+              (now + 0.01, ["1950", "1965", "650.5", "0x4", "Not Active", "Not Active", "Not Active", "Active"])]
+    c.mark(); c.t1 = now + 1.0
+    s = c.summary()
+    assert s["sm_mhz"] == 1950.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"] and s["samples"] == 1
+    assert s["samples_incl_warmup"] == 2 and s["sm_mhz_min_incl_warmup"] == 1950.0
