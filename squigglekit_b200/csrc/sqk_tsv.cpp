@@ -379,7 +379,8 @@ void sqk_score_hits(const void *hits_v, int64_t n_reads, int n_models, const dou
 {
     if (!hits_v || !mod_mean || !mod_stdev || !zs || !ps || !hps || n_reads <= 0 || n_models <= 0) return;
     const sqk_hit *hits = (const sqk_hit *)hits_v;
-    const int nt = host_threads(n_threads);
+    // (~20 ns per record: a team of threads only pays for itself on large batches)
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(n_threads), n_reads * n_models / 65536));
     (void)nt;
 #pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t r = 0; r < n_reads; r++)
