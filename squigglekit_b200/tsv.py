@@ -125,7 +125,16 @@ class Reader:
         self.pos = 0
         self.eof = False
 
+    def _stop_helper(self):
+        helper, self._helper = getattr(self, "_helper", None), None
+        if helper is not None:
+            t, stop, free = helper
+            stop.set()
+            free.put(None)
+            t.join()
+
     def close(self):
+        self._stop_helper()
         if self.fh is not None:
             self.fh.close()
         if self.mm is not None:
@@ -192,6 +201,7 @@ class Reader:
                 done.put(e)
 
         t = threading.Thread(target=work, name="sqk-tsv-prefetch", daemon=True)
+        self._helper = (t, stop, free)                       # close() stops it before the buffers go away
         t.start()
         try:
             while True:
@@ -208,9 +218,7 @@ class Reader:
                     mv.release()
                 free.put(k)                                 # the caller is done with that batch: its slot may be refilled
         finally:
-            stop.set()
-            free.put(None)
-            t.join()
+            self._stop_helper()
 
     def _fill(self):
         if self.pos:

@@ -212,3 +212,25 @@ def test_prefetch_reader_equals_plain_reader(tmp_path):
         with pytest.raises(ValueError):
             list(rd)
     assert threading.active_count() == before
+
+
+def test_prefetch_reader_consumer_error_and_close(tmp_path):
+    """An exception in the consuming loop, or close() while a batch is pending, stops the helper thread before the sample
+    buffer is released."""
+    import threading
+    lines = ["\t".join([f"f{i}.fast5", f"r{i}"] + ["5"] * 20) for i in range(500)]
+    path = tmp_path / "e.tsv"
+    path.write_bytes(("\n".join(lines) + "\n").encode())
+    before = threading.active_count()
+    with pytest.raises(RuntimeError):
+        with tsv.Reader(str(path), 2, max_lines=10, pinned=False) as rd:
+            for k, b in enumerate(rd):
+                if k == 1:
+                    raise RuntimeError("consumer failed")
+    assert threading.active_count() == before
+    rd = tsv.Reader(str(path), 2, max_lines=10, pinned=False)
+    it = iter(rd)
+    next(it)
+    rd.close()                                               # generator still alive: close() must not leave the thread behind
+    assert threading.active_count() == before
+    del it
