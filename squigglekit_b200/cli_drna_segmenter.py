@@ -61,6 +61,34 @@ def flush_tsv(ctx, cfg, names, sigs, out):
     names.clear(); sigs.clear()
 
 
+def run_signal_file(ctx, args, cfg, out):
+    """-s input through the batched text reader (squigglekit_b200.tsv): a batch of plain int16 lines goes from the parsed
+    buffer straight into one sqk_rollmean call; a batch with anything else in it takes the per-line path, int() per field as
+    the reference does (:278; values beyond int16 are outliers either way)."""
+    from . import tsv
+    with tsv.Reader(args.signal, args.start_col, max_lines=BATCH_READS, max_samples=BATCH_SAMPLES) as rd:
+        for b in rd:
+            if not b.status.any():
+                segs, found = ctx.rollmean(b.signals[:int(b.offsets[b.n])], b.offsets, cfg)
+                heads = b.heads(2)
+                for r in np.flatnonzero(np.asarray(found) > 0):
+                    h = heads[r]
+                    out.write("{}\t{}\t{}\t{}\n".format(h[0], h[1] if len(h) > 1 else "", int(segs[r, 0]), int(segs[r, 1])))
+                continue
+            names, sigs = [], []
+            for i in range(b.n):
+                h = b.head(i)
+                if b.status[i] & tsv.NO_SIGNAL:
+                    sig = np.zeros(0, dtype=np.int16)            # (the reference would look at an empty list: no segment)
+                elif b.status[i] & tsv.NOT_INT16:
+                    sig = np.clip(np.array([int(v) for v in b.tail_text(i).split("\t") if v != ""], dtype=np.int64),
+                                  -32768, 32767).astype(np.int16)
+                else:
+                    sig = b.sig(i).copy()
+                names.append((h[0], h[1] if len(h) > 1 else "")); sigs.append(sig)
+            flush_tsv(ctx, cfg, names, sigs, out)
+
+
 def main(argv=None, out=sys.stdout):
     parser = build_parser()
     args = parser.parse_args(argv)
@@ -77,16 +105,8 @@ def main(argv=None, out=sys.stdout):
             parser.print_help(sys.stderr)
             sys.exit(1)
         cfg = sqk.RollmeanConfig(w=args.window)
-        with sqk.Context(0) as ctx, open(args.signal, "rt") as fh:
-            for line in fh:
-                cols = line.rstrip("\n").split("\t")
-                # int() per field as the reference does (:278); values beyond int16 are outliers either way
-                sig = np.clip(np.array([int(v) for v in cols[args.start_col:]], dtype=np.int64), -32768, 32767).astype(np.int16)
-                names.append((cols[0], cols[1])); sigs.append(sig)
-                pending += sig.size
-                if pending >= BATCH_SAMPLES or len(names) >= BATCH_READS:
-                    flush_tsv(ctx, cfg, names, sigs, out); pending = 0
-            flush_tsv(ctx, cfg, names, sigs, out)
+        with sqk.Context(0) as ctx:
+            run_signal_file(ctx, args, cfg, out)
         return
     with sqk.Context(0) as ctx:
         for rec in slow5.read_blow5(args.slow5):

@@ -124,3 +124,40 @@ def test_segmenter_signal_file_flow(tmp_path, pageable, monkeypatch, capsys, fla
         want.append(f5 + "\t" + ",".join(str(v) for ij in found for v in ij))
     got = out.getvalue().rstrip("\n").split("\n") if out.getvalue() else []
     assert got == want
+
+
+def test_drna_segmenter_signal_file_flow(tmp_path, pageable, golden_dir, monkeypatch):
+    """dRNA_segmenter.py -s: the golden reads (segments produced by the reference's own loop body with real pandas) through
+    the batched reader, with one line that is not plain int16 (it takes the per-line path) and small batches."""
+    import importlib.util
+    import json
+    import os
+    from squigglekit_b200 import cli_drna_segmenter
+    spec = importlib.util.spec_from_file_location("rollmean_inputs", os.path.join(golden_dir, "rollmean_inputs.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    reads = mod.reads()[:12]
+    want = json.load(open(os.path.join(golden_dir, "rollmean_golden.json")))["segments"][:12]
+    path = tmp_path / "sig.tsv"
+    with open(path, "w") as fh:
+        for i, r in enumerate(reads):
+            vals = [str(int(v)) for v in r]
+            if i == 5 and not 0 < int(vals[7]) < 1200:
+                vals[7] = "40000"                               # an outlier beyond int16: the line is flagged, parsed with int() and clipped
+            elif i == 5:
+                vals.insert(7, "40000")                         # (an extra outlier sample does not change the kept samples)
+            fh.write("\t".join([f"f{i}.fast5", f"read{i}", "a", "b"] + vals) + "\n")
+
+    class Ctx(OracleContext):
+        def rollmean(self, signals, offsets, cfg, **kw):
+            self.calls += 1
+            ocfg = oracle.RollmeanCfg(cfg.w, cfg.seg_dist, cfg.lo_thresh, cfg.hi_thresh, cfg.shift, cfg.std_factor)
+            return oracle.rollmean_batch(np.asarray(signals), np.asarray(offsets), ocfg, lim_lo=cfg.lim_low, lim_hi=cfg.lim_hi)
+
+    monkeypatch.setattr(cli_drna_segmenter, "BATCH_READS", 4)
+    args = cli_drna_segmenter.build_parser().parse_args(["-s", str(path)])
+    out = io.StringIO()
+    ctx = Ctx()
+    cli_drna_segmenter.run_signal_file(ctx, args, sqk.RollmeanConfig(w=args.window), out)
+    assert ctx.calls >= 3
+    exp = [f"f{i}.fast5\tread{i}\t{w[0]}\t{w[1]}" for i, w in enumerate(want) if w is not None]
+    assert [l for l in out.getvalue().split("\n") if l] == exp
