@@ -148,7 +148,12 @@ int sqk_tsv_parse(const char *text, int64_t n_bytes, int is_final, int start_col
     {
         const char *first = n_bytes > 0 ? (const char *)memchr(text, '\n', (size_t)n_bytes) : nullptr;
         const int64_t l1 = first ? (first - text) + 1 : n_bytes;
-        const double want = (double)l1 * (double)max_lines * 1.125 + 65536.0;
+        // lines the sample buffer can take if they all look like the first one (the batch ends there anyway)
+        int64_t tabs1 = 0;
+        for (int64_t i = 0; i < l1; i++) tabs1 += text[i] == '\t';
+        const int64_t fields1 = std::max<int64_t>(1, tabs1 + 1 - start_col);
+        const int64_t lines_est = std::min<int64_t>(max_lines, max_samples / fields1 + 2);
+        const double want = (double)l1 * (double)lines_est * 1.125 + 65536.0;
         const int64_t step = want > 4e18 ? n_bytes : std::max<int64_t>((int64_t)want, 1 << 20);
         int64_t scanned = 0;
         while (scanned < n_bytes && (int64_t)nlpos.size() < max_lines) {
