@@ -4,8 +4,9 @@
 // What changed against the second generation (profiles/r02_stats2_*: 5.5 k warp-instructions per 4096-sample read in
 // zscale mode, 9.5 k in segmenter mode, 21-24 of 32 lanes active, six CTA barriers per read):
 //   * a warp owns a read from the bulk copy to the result: no CTA barrier anywhere, no cross-warp reduction through
-//     shared memory, every phase hand-over is a __syncwarp.  The CTA is one warp; each keeps two staging buffers, the
-//     next read's bulk copy (cp.async.bulk + mbarrier) is issued before the current read is touched.
+//     shared memory, every phase hand-over is a __syncwarp.  The CTA is one warp with ONE staging buffer (shared memory per
+//     warp limits the warps per SM, and the phases are dependent chains that need warps); the next read's bulk copy
+//     (cp.async.bulk + mbarrier) is issued as soon as the last pass over the staged samples is done.
 //   * the pairwise tree (numpy's order, sqk_stats_plan.cuh) is walked from a DENSE list of leaves: one 32-bit word per
 //     leaf (shared address of its first sample | length | slot), built once per read with ballots.  Leaves that contain an
 //     outlier are compacted in place first (inside their own span of the staged read; the exception list is rewritten to
