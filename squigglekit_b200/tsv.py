@@ -109,7 +109,8 @@ class Reader:
                     pass
                 self.mm_arr = np.frombuffer(self.mm, dtype=np.uint8)
             self.size = size
-        self.prefetch = bool(prefetch) and self.fh is None and self.max_samples >= 16
+        self.prefetch = (bool(prefetch) and self.fh is None and self.max_samples >= 16
+                         and os.environ.get("SQK_TSV_PREFETCH", "1") != "0")     # (knob: single buffer, no helper thread)
         n_slots = 2 if self.prefetch else 1
         self.slot_samples = (self.max_samples // n_slots) & ~7 if n_slots > 1 else self.max_samples
         self._pinned = None
