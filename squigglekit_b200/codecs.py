@@ -98,8 +98,8 @@ def svb_decode(data, count: int):
     -> (uint32 [count], bytes consumed)."""
     buf = np.frombuffer(bytes(data), dtype=np.uint8)
     n_ctrl = (count + 3) // 4
-    if buf.size < n_ctrl:
-        raise CodecError("StreamVByte stream shorter than its control bytes")
+    if count < 0 or buf.size < n_ctrl + count:                # (every value has a control code and at least one data byte)
+        raise CodecError("StreamVByte stream shorter than its value count allows")
     ctrl = buf[:n_ctrl]
     codes = ((ctrl[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(-1)[:count].astype(np.int64)
     lens = codes + 1

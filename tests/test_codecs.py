@@ -175,3 +175,22 @@ def test_blow5_refuses_what_it_does_not_know(tmp_path):
     p.write_bytes(bytes(bad))
     with pytest.raises(slow5.Slow5Error):
         list(slow5.read_blow5(str(p)))
+
+
+def test_corrupt_streams_raise_instead_of_allocating():
+    """A count that the stream cannot possibly hold (a corrupt header) is refused before anything is sized by it."""
+    with pytest.raises(codecs.CodecError):
+        codecs.svb_decode(b"\x00" * 10, 1 << 31)
+    with pytest.raises(codecs.CodecError):
+        codecs.svb_zd_decode(struct.pack("<I", 1 << 30) + b"\x00" * 16, 1 << 30)
+    with pytest.raises(codecs.CodecError):
+        codecs.vbz_decode(struct.pack("<I", 0xFFFFFFF0) + zstd(b"\x00" * 8), (0, 2, 1, 1), 2)
+    rng = np.random.default_rng(9)
+    for _ in range(200):                                      # random garbage: an error or some array, never a crash
+        blob = rng.integers(0, 256, int(rng.integers(0, 64)), dtype=np.uint8).tobytes()
+        n = int(rng.integers(0, 80))
+        try:
+            v, used = codecs.svb_decode(blob, n)
+            assert v.size == n and used <= len(blob)
+        except codecs.CodecError:
+            pass
